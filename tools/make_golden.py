@@ -1,0 +1,74 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (exec'd from /root/reference via
+oracle/ref_loader.py).  Run here (the GPU box has no /root/reference):  python tools/make_golden.py
+The fixtures pin oracle/conformer_oracle.py (tests/test_oracle_pin.py) and travel to the GPU box."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_loader as rl  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def sd_np(sd):
+    return {f"sd::{k}": v.detach().cpu().numpy() for k, v in sd.items()}
+
+
+def gen_mel():
+    ref = rl.load()
+    torch.manual_seed(7)
+    fb = ref.FilterbankFeatures(sample_rate=16000, n_window_size=400, n_window_stride=160, n_fft=512, nfilt=80,
+                                dither=1e-5, pad_to=0, normalize="per_feature")
+    fb.eval()
+    x = torch.rand(3, 8000) * 0.2 - 0.1
+    length = torch.tensor([8000, 5280, 799])
+    mel, seq = fb(x.clone(), length)
+    fbn = ref.FilterbankFeatures(sample_rate=16000, n_window_size=400, n_window_stride=160, n_fft=512, nfilt=80,
+                                 dither=1e-5, pad_to=0, normalize=None)
+    fbn.eval()
+    mel_raw, _ = fbn(x.clone(), length)
+    lens = torch.cat([torch.arange(0, 1200), torch.randint(0, 2_000_000, (800,))])
+    np.savez_compressed(os.path.join(OUT, "mel.npz"), x=x.numpy(), length=length.numpy(), mel=mel.numpy(),
+                        mel_raw=mel_raw.numpy(), seq_len=seq.numpy(), fb=fb.fb[0].numpy(), window=fb.window.numpy(),
+                        lens=lens.numpy(), lens_out=fb.get_seq_len(lens).numpy())
+
+
+def gen_encoder(name, **kw):
+    cfg = dict(feat_in=80, n_layers=2, d_model=32, n_heads=4, conv_kernel_size=9, dropout=0.0,
+               dropout_pre_encoder=0.0, dropout_emb=0.0, dropout_att=0.0)
+    cfg.update(kw)
+    enc = rl.make_encoder(seed=3, **cfg)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 80, 131, generator=g)
+    length = torch.tensor([131, 97, 40])
+    # zero padded frames like the preprocessor does
+    for b in range(3):
+        x[b, :, length[b]:] = 0
+    enc.eval()
+    with torch.no_grad():
+        y_eval, ylen = enc(audio_signal=x, length=length)
+    sd0 = {k: v.clone() for k, v in enc.state_dict().items()}
+    enc.train()
+    y_train, _ = enc(audio_signal=x, length=length)
+    # NB: mean(y^2) is ~invariant under the final LayerNorm (zero gradient) — use a fixed random projection
+    r = torch.randn(y_train.shape, generator=g)
+    loss = (y_train.float() * r).sum() / y_train.shape[0]
+    loss.backward()
+    grads = {f"grad::{k}": p.grad.detach().numpy() for k, p in enc.named_parameters()}
+    bn = {f"bn::{k}": v.detach().numpy() for k, v in enc.state_dict().items() if "running_" in k}
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), x=x.numpy(), length=length.numpy(),
+                        y_eval=y_eval.numpy(), y_train=y_train.detach().numpy(), ylen=ylen.numpy(),
+                        loss=loss.detach().numpy(), r=r.numpy(), **sd_np(sd0), **grads, **bn)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    gen_mel()
+    gen_encoder("enc_striding", subsampling="striding", subsampling_factor=4)
+    gen_encoder("enc_dw_striding", subsampling="dw_striding", subsampling_factor=8, subsampling_conv_channels=16,
+                n_heads=2)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
