@@ -1,0 +1,159 @@
+/* libb200conformer — C ABI of the B200-native Conformer-ASR encoder hot path.
+ *
+ * The reference (NVIDIA-NeMo/NeMo) has no C/FFI plugin interface for this path: its boundary is the Python
+ * module contract of `AudioToMelSpectrogramPreprocessor.forward` (nemo/collections/asr/modules/audio_preprocessing.py:93-103)
+ * and `ConformerEncoder.forward` (nemo/collections/asr/modules/conformer_encoder.py:548-591), whose arithmetic
+ * executes in torch ops (cuFFT / cuDNN / cuBLAS / ATen).  This header is the thin C ABI *under* that Python
+ * boundary: plain device pointers + sizes, caller-owned memory, an explicit CUDA stream, no torch
+ * types, no allocation, no implicit synchronisation.  `nemo_b200/` binds it with ctypes; INTEGRATION.md shows the
+ * binding a NeMo maintainer would add.
+ *
+ * Every function returns B2C_OK (0) or a negative error code; `b2c_last_error()` returns a thread-local message.
+ * All pointers are DEVICE pointers unless stated otherwise.  `stream` is a cudaStream_t passed as void*.
+ */
+#ifndef B200CONFORMER_H_
+#define B200CONFORMER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2C_OK 0
+#define B2C_ERR_INVALID (-1)
+#define B2C_ERR_CUDA (-2)
+#define B2C_ERR_UNSUPPORTED (-3)
+
+const char* b2c_last_error(void);
+int b2c_version(void);
+/* number of kernels this library has launched since load (bench.py's `gpu_launches`). */
+long long b2c_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------ GEMM core
+ * D[M,N] = sum_k A(m,k) B(n,k), bf16 operands, fp32 accumulation (tcgen05 / TMEM), fused epilogue.
+ * a_mn_major = 0: A is [M, K] row-major (K contiguous, pitch lda elements); 1: A is [K, M] row-major.
+ * b_mn_major likewise for B ([N, K] vs [K, N]).
+ * Replaces nn.Linear / 1x1 Conv1d forward and autograd on the hot path (conformer_modules.py:322,347,382-387;
+ * multi_head_attention.py:104-123,146,300; subsampling.py:431). */
+typedef enum {
+  B2C_EPI_BF16 = 0,      /* out0(bf16)[m,n] = acc + bias[n]                                               */
+  B2C_EPI_SILU = 1,      /* out0 = z = bf16(acc+bias); out1 = bf16(dropout(silu(z)))        (FFN linear1)  */
+  B2C_EPI_RESID_F32 = 2, /* out0(f32) = (aux? aux(f32) : 0) + alpha * dropout(bf16(acc+bias))  (residual)  */
+  B2C_EPI_GLU_MASK = 3,  /* interleaved (value,gate) columns: out0 = bf16(acc+bias) [M,N];
+                            out1[m,n/2] = bf16(a*sigmoid(g)) * (t<len)                (pointwise_conv1+GLU) */
+  B2C_EPI_DSILU = 4,     /* out0 = bf16(dropout(bf16(acc)) * silu'(aux(bf16)[m,n]))        (FFN backward)  */
+  B2C_EPI_RELU_MASK = 5, /* out0 = bf16(relu(acc+bias)) * (t<len)                      (subsampling conv) */
+  B2C_EPI_ACCUM_F32 = 6  /* out0(f32)[m,n] += alpha*acc  (split-K, atomic)             (weight gradients)  */
+} b2c_epilogue_mode;
+
+typedef struct {
+  void* out0;
+  void* out1;
+  const void* aux;
+  const float* bias;      /* [N] fp32 or NULL */
+  const int32_t* lengths; /* [B] valid rows per batch item (GLU/RELU masks) or NULL */
+  long long ldo;          /* pitch (elements) of out0 / aux */
+  int rows_per_batch;     /* rows of the GEMM per batch item (T, or T*rows_inner) */
+  int rows_inner;         /* RELU_MASK: rows per time step (F) */
+  float alpha;
+  unsigned long long seed; /* dropout: Philox key */
+  unsigned int drop_site;  /* dropout: site id (layer*16 + site) */
+  unsigned int drop_keep;  /* dropout: keep threshold = (1-p)*2^32, 0 = no dropout */
+  float drop_scale;        /* 1/(1-p) */
+} b2c_epilogue;
+
+int b2c_gemm(const void* A, const void* B, int M, int N, int K, int lda, int ldb, int a_mn_major, int b_mn_major,
+             int epilogue_mode, const b2c_epilogue* epi, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ mel front-end
+ * Fused FilterbankFeatures.forward (nemo/collections/asr/parts/preprocessing/features.py:423-502), eval/no-dither
+ * or dither via `dither`>0 with Philox(seed): pre-emphasis, length mask, centred 512-pt STFT (hann 400, hop 160),
+ * power, Slaney mel (sparse), log(x+2^-24), per-feature normalisation (unbiased std + 1e-5), frame masking.
+ *   x [B,S] f32, length [B] i64  →  mel [B,n_mels,T] f32 (T = S/hop+1), seq_len [B] i64.
+ * `fb` is the dense [n_mels, n_fft/2+1] f32 filterbank buffer (state_dict `featurizer.fb`), `window` [win] f32,
+ * `fb_ranges` [n_mels*2] i32 = per-filter [first, last+1) non-zero bin, prepared once by b2c_mel_fb_ranges. */
+int b2c_mel_seq_len(const int64_t* length, int64_t* seq_len, int B, int n_fft, int hop, void* stream);
+int b2c_mel_fb_ranges(const float* fb, int n_mels, int n_bins, int32_t* ranges, void* stream);
+int b2c_mel_frontend(const float* x, const int64_t* length, const float* window, const float* fb,
+                     const int32_t* fb_ranges, float* mel, int64_t* seq_len, int B, int S, int T, int n_mels, int win,
+                     int hop, int n_fft, float preemph, float dither, unsigned long long seed, int normalize,
+                     float pad_value, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ elementwise / norm
+ * LayerNorm over the last dim (eps 1e-5), fp32 in → bf16 out (+ optional fp32 out), saves mean / rstd per row.
+ * torch.nn.LayerNorm under bf16 autocast (conformer_modules.py:94-158). */
+int b2c_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,
+                      float* rstd, int M, int d, void* stream);
+/* dy (bf16 if dy_is_bf16 else f32) → dx: dr[m,:] (+)= LN'(dy); dgamma/dbeta += ; optionally emits
+ * next_bf16 = bf16(next_scale * dr) (the gradient entering the previous sub-block's output GEMM). */
+int b2c_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* gamma, const float* mean,
+                      const float* rstd, float* dr, int accumulate, float* dgamma, float* dbeta, void* next_bf16,
+                      float next_scale, float drop_p, unsigned long long seed, unsigned int site, int M, int d,
+                      void* stream);
+/* out_f32[n] += sum_m in_bf16[m,n]  (bias gradients) */
+int b2c_colsum_bf16(const void* in_bf16, float* out, int M, int N, int ld, void* stream);
+/* fp32 → bf16 cast with optional scale */
+int b2c_cast_bf16(const float* in, void* out_bf16, long long n, float scale, void* stream);
+/* in [A,B,C] f32 → out permuted; mode 0: out[b][a][c]; mode 1: out[a][c][b].  Weight layout preparation
+ * (GLU value/gate interleave, conv taps-major, flatten order) and the inverse for their gradients. */
+int b2c_permute3_bf16(const float* in, void* out_bf16, int A, int B, int C, int mode, void* stream);
+int b2c_permute3_f32(const float* in, float* out, int A, int B, int C, int mode, int accumulate, void* stream);
+int b2c_fill_f32(float* p, long long n, float v, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ conv module
+ * Depthwise k-tap conv over time (symmetric pad (k-1)/2) + bias on channels-last [B*T, d] bf16 with per-channel
+ * sum / sum-of-squares accumulation for BatchNorm (causal_convs.py:130-150, conformer_modules.py:332-342). */
+int b2c_dwconv_fwd(const void* u_bf16, const float* w, const float* bias, void* c_bf16, float* bn_sum, float* bn_sumsq,
+                   int B, int T, int d, int k, void* stream);
+/* BatchNorm1d finalise: train → batch mean/var (biased) into scale/shift and momentum update of running stats
+ * (unbiased var); eval → running stats.  scale = gamma*rstd, shift = beta - mean*scale. */
+int b2c_bn_finalize(const float* bn_sum, const float* bn_sumsq, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float* scale, float* shift, float* mean_out,
+                    float* rstd_out, long long count, int d, int training, float momentum, float eps, void* stream);
+/* s = bf16(silu(bf16(c*scale+shift))) */
+int b2c_bn_silu_fwd(const void* c_bf16, const float* scale, const float* shift, void* s_bf16, long long M, int d,
+                    void* stream);
+/* BN(train)+SiLU backward, phase 1: per-channel sums of dz and dz*xhat (dz = ds*silu'(bn) ) */
+int b2c_bn_silu_bwd_reduce(const void* ds_bf16, const void* c_bf16, const float* scale, const float* shift,
+                           const float* mean, const float* rstd, float* sum_dz, float* sum_dz_xhat, long long M, int d,
+                           void* stream);
+/* phase 2: dc = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)) (train) or gamma*rstd*dz (eval); also dgamma/dbeta */
+int b2c_bn_silu_bwd_apply(const void* ds_bf16, const void* c_bf16, const float* gamma, const float* scale,
+                          const float* shift, const float* mean, const float* rstd, const float* sum_dz,
+                          const float* sum_dz_xhat, void* dc_bf16, float* dgamma, float* dbeta, long long M, int d,
+                          int training, void* stream);
+/* depthwise conv backward: du (masked by t<len), dw [d,k], dbias [d] */
+int b2c_dwconv_bwd(const void* dc_bf16, const void* u_bf16, const float* w, const int32_t* lengths, void* du_bf16,
+                   float* dw, float* dbias, int B, int T, int d, int k, void* stream);
+/* GLU backward on interleaved (value,gate) layout: dg[m,2j] = du*sig(g); dg[m,2j+1] = du*a*sig(g)(1-sig(g)) */
+int b2c_glu_bwd(const void* du_bf16, const void* g_bf16, void* dg_bf16, long long M, int d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ attention
+ * Transformer-XL relative-position attention, flash-style (nothing [T,T]-shaped touches HBM):
+ *   S[i,j] = ((q_i+u).k_j + (q_i+v).p[T-1-i+j]) / sqrt(dk);  masked_fill(-1e4); softmax; masked_fill(0); dropout; PV
+ * (multi_head_attention.py:125-146,259-354).  qkv [B*T, 3*d] bf16 (q | k | v), pos [2T-1, d] bf16,
+ * pos_bias_u/v [h, dk] f32, lengths [B] i32.  ctx [B*T, d] bf16, lse [B, h, T] f32. */
+int b2c_relpos_attn_fwd(const void* qkv, const void* pos, const float* bias_u, const float* bias_v,
+                        const int32_t* lengths, void* ctx, float* lse, int B, int T, int h, int dk, float drop_p,
+                        unsigned long long seed, unsigned int site, void* stream);
+size_t b2c_relpos_attn_bwd_workspace(int B, int T, int h);
+int b2c_relpos_attn_bwd(const void* qkv, const void* pos, const float* bias_u, const float* bias_v,
+                        const int32_t* lengths, const void* ctx, const void* dctx, const float* lse, void* dqkv,
+                        float* dpos_f32, float* dbias_u, float* dbias_v, void* workspace, size_t workspace_bytes,
+                        int B, int T, int h, int dk, float drop_p, unsigned long long seed, unsigned int site,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------ misc
+ * relative positional table rows = positions T-1 … -(T-1) (multi_head_attention.py:1007-1020,1056-1100) */
+int b2c_relpos_table(void* pos_bf16, float* pos_f32, int T, int d, void* stream);
+/* lengths after n stride-2 3x3 pad-1 convs: (L+2-3)//2+1 (subsampling.py:576-586,720-722).
+ * len_in32 [B] = int32 copy of the input, len_stage [n_convs*B] int32 per stage, len_out64 [B]. */
+int b2c_subsample_lengths(const int64_t* len_in, int32_t* len_in32, int32_t* len_stage, int64_t* len_out64, int B,
+                          int n_convs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CONFORMER_H_ */

@@ -1,0 +1,710 @@
+// K5: Transformer-XL relative-position multi-head attention, flash-style (nothing [T,T]-shaped is kept in the
+// forward; the backward stages dS / P tiles once in bf16 for the key-side and position-side reductions).
+//
+//   S[i,j] = ((q_i + u) . k_j  +  (q_i + v) . p[T-1-i+j]) / sqrt(dk)          rel_shift folded into the band index
+//   S = masked_fill(S, ~(valid_i & valid_j), -1e4); A = softmax(S); A = masked_fill(A, mask, 0); A = dropout(A)
+//   ctx = A V
+// Reference: RelPositionMultiHeadAttention.forward / rel_shift / forward_attention,
+//            nemo/collections/asr/parts/submodules/multi_head_attention.py:125-146,259-354.
+//
+// Round-1 implementation: warp-level mma.sync.m16n8k16 (bf16, fp32 accumulate) with the positional band of
+// 16+64-1 rows per warp multiplied on tensor cores and skewed through a per-warp shared-memory scratch.
+// (tcgen05/TMEM version of this kernel is the next optimisation step; see DESIGN.md.)
+#include "common.cuh"
+
+namespace b2c {
+
+constexpr int BQ = 64;    // query rows per CTA (4 warps x 16)
+constexpr int BKV = 64;   // keys per inner tile
+constexpr int BAND = 80;  // 16 + 64 - 1 rounded up to a multiple of 16
+constexpr int SCR_PITCH = 84;
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+
+struct AttnArgs {
+  const bf16* qkv;   // [B*T, 3d]
+  const bf16* pos;   // [2T-1, d]
+  const float* bias_u;
+  const float* bias_v;
+  const int32_t* lengths;
+  int B, T, H, d;
+  float scale;       // 1/sqrt(dk)
+  float drop_p;
+  unsigned int drop_keep;
+  float drop_scale;
+  unsigned long long seed;
+  unsigned int site;
+};
+
+// ---- tile loaders -------------------------------------------------------------------------------------------
+// rows [row0, row0+nrows) x DK columns of a [*, ld] bf16 matrix into smem (pitch DK+8); rows outside [0, limit) → 0
+template <int DK>
+__device__ __forceinline__ void load_tile(bf16* s, const bf16* g, long long row0, int nrows, long long limit, int ld,
+                                          int tid, int nthreads) {
+  constexpr int P = DK + 8;
+  constexpr int VPR = DK / 8;  // 16-byte vectors per row
+  for (int i = tid; i < nrows * VPR; i += nthreads) {
+    const int r = i / VPR, v = i - r * VPR;
+    const long long gr = row0 + r;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (gr >= 0 && gr < limit) val = *reinterpret_cast<const uint4*>(g + gr * ld + v * 8);
+    *reinterpret_cast<uint4*>(s + r * P + v * 8) = val;
+  }
+}
+
+// A fragments (16 rows x DK) of bf16(q + bias) for this warp, straight from global.  rows >= T → 0
+template <int DK>
+__device__ __forceinline__ void load_q_frags(uint32_t (&fr)[DK / 16][4], const bf16* q, int ld, int row0, int T,
+                                             const float* bias, int lane) {
+  const int g = lane >> 2, c = lane & 3;
+#pragma unroll
+  for (int ks = 0; ks < DK / 16; ++ks) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {    // k offset 0 / 8
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {        // row g / g+8
+        const int row = row0 + g + rr * 8;
+        const int col = ks * 16 + half * 8 + 2 * c;
+        uint32_t out = 0u;
+        if (row < T) {
+          float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(q + (size_t)row * ld + col));
+          if (bias) { v.x += bias[col]; v.y += bias[col + 1]; }
+          out = pack_bf16(v.x, v.y);
+        }
+        fr[ks][half * 2 + rr] = out;
+      }
+    }
+  }
+}
+
+// S(16 x 64) (+)= A(16 x DK) * Bt where Bt rows (keys / band rows) live in smem [row][DK+8]
+template <int DK, int NT>
+__device__ __forceinline__ void mma_qk(float (&acc)[NT][4], const uint32_t (&a)[DK / 16][4], const bf16* sB, int lane) {
+  constexpr int P = DK + 8;
+  const int g = lane >> 2, c = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+    for (int ks = 0; ks < DK / 16; ++ks) {
+      const bf16* p = sB + (nt * 8 + g) * P + ks * 16 + 2 * c;
+      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(p);
+      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(p + 8);
+      mma16816(acc[nt], a[ks], b0, b1);
+    }
+  }
+}
+
+// O(16 x DK) += A(16 x KROWS) * B where B rows (k) live in smem [k][DK+8]; A given as bf16 fragments per 16-k step
+template <int DK, int KSTEPS>
+__device__ __forceinline__ void mma_pv(float (&o)[DK / 8][4], const uint32_t (&a)[KSTEPS][4], const bf16* sB, int lane) {
+  constexpr int P = DK + 8;
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks) {
+#pragma unroll
+    for (int nt = 0; nt < DK / 8; ++nt) {
+      uint32_t b0, b1;
+      ldsm_x2_trans(b0, b1, sB + (ks * 16 + (lane & 15)) * P + nt * 8);
+      mma16816(o[nt], a[ks], b0, b1);
+    }
+  }
+}
+
+// Recompute one 16x64 score tile for this warp: raw = ac + skew(bd), (NOT yet scaled)
+template <int DK>
+__device__ __forceinline__ void score_tile(float (&s)[8][4], const uint32_t (&qu)[DK / 16][4],
+                                           const uint32_t (&qv)[DK / 16][4], const bf16* sK, const bf16* sP, float* scr,
+                                           int warp, int lane) {
+  const int g = lane >> 2, c = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+  mma_qk<DK, 8>(s, qu, sK, lane);
+  float r[BAND / 8][4];
+#pragma unroll
+  for (int nt = 0; nt < BAND / 8; ++nt) r[nt][0] = r[nt][1] = r[nt][2] = r[nt][3] = 0.f;
+  mma_qk<DK, BAND / 8>(r, qv, sP + (3 - warp) * 16 * (DK + 8), lane);
+  __syncwarp();
+#pragma unroll
+  for (int nt = 0; nt < BAND / 8; ++nt) {
+    *reinterpret_cast<float2*>(scr + g * SCR_PITCH + nt * 8 + 2 * c) = make_float2(r[nt][0], r[nt][1]);
+    *reinterpret_cast<float2*>(scr + (g + 8) * SCR_PITCH + nt * 8 + 2 * c) = make_float2(r[nt][2], r[nt][3]);
+  }
+  __syncwarp();
+  // bd[il][jl] = R[il][jl + 15 - il]
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    const int col = nt * 8 + 2 * c;
+    s[nt][0] += scr[g * SCR_PITCH + col + 15 - g];
+    s[nt][1] += scr[g * SCR_PITCH + col + 1 + 15 - g];
+    s[nt][2] += scr[(g + 8) * SCR_PITCH + col + 15 - (g + 8)];
+    s[nt][3] += scr[(g + 8) * SCR_PITCH + col + 1 + 15 - (g + 8)];
+  }
+}
+
+__device__ __forceinline__ bool attn_keep(const AttnArgs& a, int b, int h, int i, int j) {
+  const uint64_t idx = ((uint64_t)((b * a.H + h) * (int64_t)a.T + i)) * (uint64_t)a.T + (uint64_t)j;
+  return dropout_keep(a.seed, a.site, idx, a.drop_keep);
+}
+
+// =============================================================================================== forward
+template <int DK>
+__global__ void __launch_bounds__(128)
+relpos_attn_fwd_kernel(const AttnArgs a, bf16* __restrict__ ctx, float* __restrict__ lse_out) {
+  constexpr int P = DK + 8;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  bf16* sK = reinterpret_cast<bf16*>(smraw);
+  bf16* sV = sK + BKV * P;
+  bf16* sP = sV + BKV * P;                               // 128 band rows
+  float* scr_all = reinterpret_cast<float*>(sP + 128 * P);  // 4 x 16 x SCR_PITCH
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+  const int i0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int T = a.T, ld = 3 * a.d;
+  const int len = a.lengths ? min(a.lengths[b], T) : T;
+  const bf16* qb = a.qkv + (size_t)b * T * ld + h * DK;
+  const bf16* kb = qb + a.d;
+  const bf16* vb = qb + 2 * a.d;
+  const bf16* pb = a.pos + h * DK;
+  float* scr = scr_all + warp * 16 * SCR_PITCH;
+
+  uint32_t qu[DK / 16][4], qv[DK / 16][4];
+  load_q_frags<DK>(qu, qb, ld, i0 + warp * 16, T, a.bias_u + h * DK, lane);
+  load_q_frags<DK>(qv, qb, ld, i0 + warp * 16, T, a.bias_v + h * DK, lane);
+
+  float o[DK / 8][4];
+#pragma unroll
+  for (int nt = 0; nt < DK / 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+  float m[2] = {-1e30f, -1e30f}, l[2] = {0.f, 0.f};
+  const int row_g[2] = {i0 + warp * 16 + g, i0 + warp * 16 + g + 8};
+  const float sc2 = a.scale * kLog2e;
+
+  const int n_kv = (len + BKV - 1) / BKV;  // keys >= len contribute exactly 0 (exp(-1e4 - m) == 0 in fp32)
+  for (int jt = 0; jt < n_kv; ++jt) {
+    const int j0 = jt * BKV;
+    __syncthreads();
+    load_tile<DK>(sK, kb, j0, BKV, T, ld, tid, 128);
+    load_tile<DK>(sV, vb, j0, BKV, T, ld, tid, 128);
+    load_tile<DK>(sP, pb, (long long)T - 1 - (i0 + 63) + j0, 128, 2LL * T - 1, a.d, tid, 128);
+    __syncthreads();
+    float s[8][4];
+    score_tile<DK>(s, qu, qv, sK, sP, scr, warp, lane);
+    // mask + online softmax (exp2 domain)
+    float mx[2] = {-1e30f, -1e30f};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = j0 + nt * 8 + 2 * c + (e & 1);
+        const int rr = e >> 1;
+        const bool valid = (j < len) && (row_g[rr] < len);
+        s[nt][e] = valid ? s[nt][e] * sc2 : -1e30f;
+        mx[rr] = fmaxf(mx[rr], s[nt][e]);
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(0xffffffffu, mx[rr], 1));
+      mx[rr] = fmaxf(mx[rr], __shfl_xor_sync(0xffffffffu, mx[rr], 2));
+    }
+    float corr[2], rs[2] = {0.f, 0.f};
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const float mn = fmaxf(m[rr], mx[rr]);
+      corr[rr] = exp2f(m[rr] - mn);
+      m[rr] = mn;
+    }
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float p[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int rr = e >> 1;
+        p[e] = (s[nt][e] > -1e29f) ? exp2f(s[nt][e] - m[rr]) : 0.f;
+        rs[rr] += p[e];
+        if (a.drop_keep != 0) {
+          const int j = j0 + nt * 8 + 2 * c + (e & 1);
+          p[e] = attn_keep(a, b, h, row_g[rr], j) ? p[e] * a.drop_scale : 0.f;
+        }
+      }
+      pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p[0], p[1]);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p[2], p[3]);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      rs[rr] += __shfl_xor_sync(0xffffffffu, rs[rr], 1);
+      rs[rr] += __shfl_xor_sync(0xffffffffu, rs[rr], 2);
+      l[rr] = l[rr] * corr[rr] + rs[rr];
+    }
+#pragma unroll
+    for (int nt = 0; nt < DK / 8; ++nt) {
+      o[nt][0] *= corr[0]; o[nt][1] *= corr[0];
+      o[nt][2] *= corr[1]; o[nt][3] *= corr[1];
+    }
+    mma_pv<DK, 4>(o, pa, sV, lane);
+  }
+  // finalise: rows >= len (fully masked queries) output exactly 0 (second masked_fill, :137-138)
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int row = row_g[rr];
+    if (row < T) {
+      const float inv = (row < len && l[rr] > 0.f) ? 1.f / l[rr] : 0.f;
+      bf16* op = ctx + ((size_t)b * T + row) * a.d + h * DK;
+#pragma unroll
+      for (int nt = 0; nt < DK / 8; ++nt)
+        *reinterpret_cast<uint32_t*>(op + nt * 8 + 2 * c) = pack_bf16(o[nt][rr * 2] * inv, o[nt][rr * 2 + 1] * inv);
+      if (c == 0 && lse_out) lse_out[((size_t)b * a.H + h) * T + row] = (row < len && l[rr] > 0.f) ? m[rr] + log2f(l[rr]) : 0.f;
+    }
+  }
+}
+
+// =============================================================================================== backward (query side)
+// CTA owns 64 query rows: recomputes S/P, dP = dO V^T, dS; accumulates dq = dS K + unskew(dS) Pband, d(bias_u/v);
+// stages dS (scaled, bf16) and P_dropped (bf16) in HBM workspaces [B,H,T,Tp] for the key-side / position-side kernels.
+template <int DK>
+__global__ void __launch_bounds__(128)
+relpos_attn_bwd_q_kernel(const AttnArgs a, const bf16* __restrict__ ctx, const bf16* __restrict__ dctx,
+                         const float* __restrict__ lse, bf16* __restrict__ dqkv, float* __restrict__ dbias_u,
+                         float* __restrict__ dbias_v, bf16* __restrict__ ws_ds, bf16* __restrict__ ws_p, int Tp) {
+  constexpr int P = DK + 8;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  bf16* sK = reinterpret_cast<bf16*>(smraw);
+  bf16* sV = sK + BKV * P;
+  bf16* sP = sV + BKV * P;
+  float* scr_all = reinterpret_cast<float*>(sP + 128 * P);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+  const int i0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int T = a.T, ld = 3 * a.d;
+  const int len = a.lengths ? min(a.lengths[b], T) : T;
+  const bf16* qb = a.qkv + (size_t)b * T * ld + h * DK;
+  const bf16* kb = qb + a.d;
+  const bf16* vb = qb + 2 * a.d;
+  const bf16* pb = a.pos + h * DK;
+  float* scr = scr_all + warp * 16 * SCR_PITCH;
+  const int wrow0 = i0 + warp * 16;
+  const int row_g[2] = {wrow0 + g, wrow0 + g + 8};
+
+  uint32_t qu[DK / 16][4], qv[DK / 16][4], dof[DK / 16][4];
+  load_q_frags<DK>(qu, qb, ld, wrow0, T, a.bias_u + h * DK, lane);
+  load_q_frags<DK>(qv, qb, ld, wrow0, T, a.bias_v + h * DK, lane);
+  load_q_frags<DK>(dof, dctx + (size_t)b * T * a.d + h * DK, a.d, wrow0, T, nullptr, lane);
+
+  // delta_i = sum_d dO[i,d] * O[i,d]
+  float delta[2] = {0.f, 0.f}, lse2[2] = {0.f, 0.f};
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int row = row_g[rr];
+    float acc = 0.f;
+    if (row < T) {
+      const bf16* op = ctx + ((size_t)b * T + row) * a.d + h * DK;
+      const bf16* dp = dctx + ((size_t)b * T + row) * a.d + h * DK;
+#pragma unroll
+      for (int nt = 0; nt < DK / 8; ++nt) {
+        const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(op + nt * 8 + 2 * c));
+        const float2 y = unpack_bf16(*reinterpret_cast<const uint32_t*>(dp + nt * 8 + 2 * c));
+        acc += x.x * y.x + x.y * y.y;
+      }
+      lse2[rr] = lse[((size_t)b * a.H + h) * T + row];
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);  // shuffles outside the divergent branch
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    delta[rr] = acc;
+  }
+
+  float dqu[DK / 8][4], dqv[DK / 8][4];
+#pragma unroll
+  for (int nt = 0; nt < DK / 8; ++nt) {
+    dqu[nt][0] = dqu[nt][1] = dqu[nt][2] = dqu[nt][3] = 0.f;
+    dqv[nt][0] = dqv[nt][1] = dqv[nt][2] = dqv[nt][3] = 0.f;
+  }
+  const float sc2 = a.scale * kLog2e;
+  bf16* wds = ws_ds + ((size_t)(b * a.H + h) * T) * Tp;
+  bf16* wp = ws_p + ((size_t)(b * a.H + h) * T) * Tp;
+  const int n_kv_all = (T + BKV - 1) / BKV;
+  const int n_kv = (len + BKV - 1) / BKV;
+  for (int jt = 0; jt < n_kv_all; ++jt) {
+    const int j0 = jt * BKV;
+    if (jt >= n_kv) {  // tiles fully beyond the valid length: dS = P = 0, just clear the workspaces
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int j = j0 + nt * 8 + 2 * c;
+          if (row_g[rr] < T && j < Tp) {
+            *reinterpret_cast<uint32_t*>(wds + (size_t)row_g[rr] * Tp + j) = 0u;
+            *reinterpret_cast<uint32_t*>(wp + (size_t)row_g[rr] * Tp + j) = 0u;
+          }
+        }
+      continue;
+    }
+    __syncthreads();
+    load_tile<DK>(sK, kb, j0, BKV, T, ld, tid, 128);
+    load_tile<DK>(sV, vb, j0, BKV, T, ld, tid, 128);
+    load_tile<DK>(sP, pb, (long long)T - 1 - (i0 + 63) + j0, 128, 2LL * T - 1, a.d, tid, 128);
+    __syncthreads();
+    float s[8][4];
+    score_tile<DK>(s, qu, qv, sK, sP, scr, warp, lane);
+    float dp[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+    mma_qk<DK, 8>(dp, dof, sV, lane);  // dP[i,j] = dO_i . V_j
+    uint32_t dsa[4][4];                // dS as A fragments (keys = k dimension)
+    __syncwarp();
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float ds[4], pd[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int rr = e >> 1;
+        const int j = j0 + nt * 8 + 2 * c + (e & 1);
+        const bool valid = (j < len) && (row_g[rr] < len);
+        float p = valid ? exp2f(s[nt][e] * sc2 - lse2[rr]) : 0.f;
+        float dpe = dp[nt][e];
+        pd[e] = p;
+        if (a.drop_keep != 0) {
+          const bool keep = valid && attn_keep(a, b, h, row_g[rr], j);
+          pd[e] = keep ? p * a.drop_scale : 0.f;
+          dpe = keep ? dpe * a.drop_scale : 0.f;
+        }
+        ds[e] = p * (dpe - delta[rr]) * a.scale;
+      }
+      dsa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(ds[0], ds[1]);
+      dsa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
+      // stage for the key-side / position-side kernels
+      const int j = j0 + nt * 8 + 2 * c;
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        if (row_g[rr] < T && j < Tp) {
+          *reinterpret_cast<uint32_t*>(wds + (size_t)row_g[rr] * Tp + j) = pack_bf16(ds[rr * 2], ds[rr * 2 + 1]);
+          *reinterpret_cast<uint32_t*>(wp + (size_t)row_g[rr] * Tp + j) = pack_bf16(pd[rr * 2], pd[rr * 2 + 1]);
+        }
+      }
+      // unskewed copy for the positional path: scr[il][jl + 15 - il] = dS[il][jl]
+      scr[g * SCR_PITCH + nt * 8 + 2 * c + 15 - g] = bf16_round(ds[0]);
+      scr[g * SCR_PITCH + nt * 8 + 2 * c + 1 + 15 - g] = bf16_round(ds[1]);
+      scr[(g + 8) * SCR_PITCH + nt * 8 + 2 * c + 15 - (g + 8)] = bf16_round(ds[2]);
+      scr[(g + 8) * SCR_PITCH + nt * 8 + 2 * c + 1 + 15 - (g + 8)] = bf16_round(ds[3]);
+    }
+    __syncwarp();
+    // dQ_u += dS K
+    mma_pv<DK, 4>(dqu, dsa, sK, lane);
+    // dQ_v += unskew(dS) (16 x 80) * Pband (80 x DK)
+    uint32_t ua[BAND / 16][4];
+#pragma unroll
+    for (int ks = 0; ks < BAND / 16; ++ks) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int il = g + rr * 8;
+          const int n = ks * 16 + half * 8 + 2 * c;
+          // valid band columns for row il: [15 - il, 15 - il + 64)
+          const int lo = 15 - il, hi = 15 - il + 64;
+          const float x0 = (n >= lo && n < hi) ? scr[il * SCR_PITCH + n] : 0.f;
+          const float x1 = (n + 1 >= lo && n + 1 < hi) ? scr[il * SCR_PITCH + n + 1] : 0.f;
+          ua[ks][half * 2 + rr] = pack_bf16(x0, x1);
+        }
+      }
+    }
+    mma_pv<DK, BAND / 16>(dqv, ua, sP + (3 - warp) * 16 * P, lane);
+  }
+  // dq = dQ_u + dQ_v → bf16 into the q slot of dqkv
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int row = row_g[rr];
+    if (row < T) {
+      bf16* op = dqkv + ((size_t)b * T + row) * ld + h * DK;
+#pragma unroll
+      for (int nt = 0; nt < DK / 8; ++nt)
+        *reinterpret_cast<uint32_t*>(op + nt * 8 + 2 * c) =
+            pack_bf16(dqu[nt][rr * 2] + dqv[nt][rr * 2], dqu[nt][rr * 2 + 1] + dqv[nt][rr * 2 + 1]);
+    }
+  }
+  // d(pos_bias_u/v)[h, col] += sum over this warp's rows
+#pragma unroll
+  for (int nt = 0; nt < DK / 8; ++nt) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float su = dqu[nt][e] + dqu[nt][e + 2];
+      float sv = dqv[nt][e] + dqv[nt][e + 2];
+#pragma unroll
+      for (int off = 4; off < 32; off <<= 1) {
+        su += __shfl_xor_sync(0xffffffffu, su, off);
+        sv += __shfl_xor_sync(0xffffffffu, sv, off);
+      }
+      if (g == 0) {
+        atomicAdd(dbias_u + h * DK + nt * 8 + 2 * c + e, su);
+        atomicAdd(dbias_v + h * DK + nt * 8 + 2 * c + e, sv);
+      }
+    }
+  }
+}
+
+// =============================================================================================== backward (key side)
+// CTA owns 64 keys of one (b,h): dK[j,:] = sum_i dS[i,j] * bf16(q_i+u);  dV[j,:] = sum_i Pd[i,j] * dO[i,:]
+template <int DK>
+__global__ void __launch_bounds__(128)
+relpos_attn_bwd_kv_kernel(const AttnArgs a, const bf16* __restrict__ dctx, const bf16* __restrict__ ws_ds,
+                          const bf16* __restrict__ ws_p, bf16* __restrict__ dqkv, int Tp) {
+  constexpr int P = DK + 8;
+  constexpr int PX = BKV + 8;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  bf16* sQ = reinterpret_cast<bf16*>(smraw);  // [64 i][DK]  bf16(q+u)
+  bf16* sO = sQ + 64 * P;                     // [64 i][DK]  dO
+  bf16* sDS = sO + 64 * P;                    // [64 i][64 j]
+  bf16* sPd = sDS + 64 * PX;                  // [64 i][64 j]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+  const int j0 = blockIdx.x * BKV, h = blockIdx.y, b = blockIdx.z;
+  const int T = a.T, ld = 3 * a.d;
+  const int len = a.lengths ? min(a.lengths[b], T) : T;
+  const bf16* qb = a.qkv + (size_t)b * T * ld + h * DK;
+  const bf16* dob = dctx + (size_t)b * T * a.d + h * DK;
+  const bf16* wds = ws_ds + ((size_t)(b * a.H + h) * T) * Tp;
+  const bf16* wp = ws_p + ((size_t)(b * a.H + h) * T) * Tp;
+  const float* bu = a.bias_u + h * DK;
+
+  float dk_[DK / 8][4], dv_[DK / 8][4];
+#pragma unroll
+  for (int nt = 0; nt < DK / 8; ++nt) {
+    dk_[nt][0] = dk_[nt][1] = dk_[nt][2] = dk_[nt][3] = 0.f;
+    dv_[nt][0] = dv_[nt][1] = dv_[nt][2] = dv_[nt][3] = 0.f;
+  }
+  const int n_q = (len + 63) / 64;  // query rows >= len have dS = P = 0
+  for (int it = 0; it < n_q; ++it) {
+    const int i0 = it * 64;
+    __syncthreads();
+    // q + u (bf16) tile
+    for (int idx = tid; idx < 64 * (DK / 2); idx += 128) {
+      const int r = idx / (DK / 2), cp = idx - r * (DK / 2);
+      uint32_t val = 0u;
+      if (i0 + r < T) {
+        float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(qb + (size_t)(i0 + r) * ld + cp * 2));
+        val = pack_bf16(v.x + bu[cp * 2], v.y + bu[cp * 2 + 1]);
+      }
+      *reinterpret_cast<uint32_t*>(sQ + r * P + cp * 2) = val;
+    }
+    load_tile<DK>(sO, dob, i0, 64, T, a.d, tid, 128);
+    for (int idx = tid; idx < 64 * 8; idx += 128) {
+      const int r = idx >> 3, v = idx & 7;
+      uint4 x = make_uint4(0, 0, 0, 0), y = make_uint4(0, 0, 0, 0);
+      if (i0 + r < T && j0 + v * 8 < Tp) {
+        x = *reinterpret_cast<const uint4*>(wds + (size_t)(i0 + r) * Tp + j0 + v * 8);
+        y = *reinterpret_cast<const uint4*>(wp + (size_t)(i0 + r) * Tp + j0 + v * 8);
+      }
+      *reinterpret_cast<uint4*>(sDS + r * PX + v * 8) = x;
+      *reinterpret_cast<uint4*>(sPd + r * PX + v * 8) = y;
+    }
+    __syncthreads();
+    // this warp's 16 keys: columns warp*16.. of sDS / sPd (A = X^T via ldmatrix.trans)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ads[4], apd[4];
+      const int mi = lane >> 3;
+      const int krow = ks * 16 + (mi >> 1) * 8 + (lane & 7);
+      const int mcol = warp * 16 + (mi & 1) * 8;
+      ldsm_x4_trans(ads, sDS + krow * PX + mcol);
+      ldsm_x4_trans(apd, sPd + krow * PX + mcol);
+#pragma unroll
+      for (int nt = 0; nt < DK / 8; ++nt) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, sQ + (ks * 16 + (lane & 15)) * P + nt * 8);
+        mma16816(dk_[nt], ads, b0, b1);
+        ldsm_x2_trans(b0, b1, sO + (ks * 16 + (lane & 15)) * P + nt * 8);
+        mma16816(dv_[nt], apd, b0, b1);
+      }
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int j = j0 + warp * 16 + g + rr * 8;
+    if (j < T) {
+      bf16* okp = dqkv + ((size_t)b * T + j) * ld + a.d + h * DK;
+      bf16* ovp = okp + a.d;
+#pragma unroll
+      for (int nt = 0; nt < DK / 8; ++nt) {
+        *reinterpret_cast<uint32_t*>(okp + nt * 8 + 2 * c) = pack_bf16(dk_[nt][rr * 2], dk_[nt][rr * 2 + 1]);
+        *reinterpret_cast<uint32_t*>(ovp + nt * 8 + 2 * c) = pack_bf16(dv_[nt][rr * 2], dv_[nt][rr * 2 + 1]);
+      }
+    }
+  }
+}
+
+// =============================================================================================== backward (position side)
+// CTA owns 64 relative-position rows r of one head: dpos[r, h*DK + :] = sum_b sum_i dS[b,h,i, i-(T-1)+r] * bf16(q_{b,i}+v)
+template <int DK>
+__global__ void __launch_bounds__(128)
+relpos_attn_bwd_pos_kernel(const AttnArgs a, const bf16* __restrict__ ws_ds, float* __restrict__ dpos, int Tp) {
+  constexpr int P = DK + 8;
+  constexpr int PX = 64 + 8;
+  extern __shared__ __align__(16) uint8_t smraw[];
+  bf16* sQ = reinterpret_cast<bf16*>(smraw);  // [64 i][DK] bf16(q+v)
+  bf16* sX = sQ + 64 * P;                     // [64 i][64 r]  diagonal gather of dS
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+  const int r0 = blockIdx.x * 64, h = blockIdx.y;
+  const int T = a.T, ld = 3 * a.d, R = 2 * T - 1;
+  const float* bv = a.bias_v + h * DK;
+  float acc[DK / 8][4];
+#pragma unroll
+  for (int nt = 0; nt < DK / 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+  // rows i that can pair with r in [r0, r0+64): j = i - (T-1) + r in [0, T)  →  i in [T-1-r0-63, 2T-2-r0]
+  const int i_lo = max(0, T - 1 - (r0 + 63)), i_hi = min(T - 1, 2 * T - 2 - r0);
+  for (int b = 0; b < a.B; ++b) {
+    const int len = a.lengths ? min(a.lengths[b], T) : T;
+    const int hi = min(i_hi, len - 1);
+    const bf16* qb = a.qkv + (size_t)b * T * ld + h * DK;
+    const bf16* wds = ws_ds + ((size_t)(b * a.H + h) * T) * Tp;
+    for (int i0 = (i_lo / 64) * 64; i0 <= hi; i0 += 64) {
+      __syncthreads();
+      for (int idx = tid; idx < 64 * (DK / 2); idx += 128) {
+        const int r = idx / (DK / 2), cp = idx - r * (DK / 2);
+        uint32_t val = 0u;
+        if (i0 + r < T) {
+          float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(qb + (size_t)(i0 + r) * ld + cp * 2));
+          val = pack_bf16(v.x + bv[cp * 2], v.y + bv[cp * 2 + 1]);
+        }
+        *reinterpret_cast<uint32_t*>(sQ + r * P + cp * 2) = val;
+      }
+      for (int idx = tid; idx < 64 * 64; idx += 128) {
+        const int il = idx >> 6, rl = idx & 63;
+        const int i = i0 + il, j = i - (T - 1) + r0 + rl;
+        bf16 v = __float2bfloat16_rn(0.f);
+        if (i < T && j >= 0 && j < T && r0 + rl < R) v = wds[(size_t)i * Tp + j];
+        sX[il * PX + rl] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t ax[4];
+        const int mi = lane >> 3;
+        ldsm_x4_trans(ax, sX + (ks * 16 + (mi >> 1) * 8 + (lane & 7)) * PX + warp * 16 + (mi & 1) * 8);
+#pragma unroll
+        for (int nt = 0; nt < DK / 8; ++nt) {
+          uint32_t b0, b1;
+          ldsm_x2_trans(b0, b1, sQ + (ks * 16 + (lane & 15)) * P + nt * 8);
+          mma16816(acc[nt], ax, b0, b1);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const int r = r0 + warp * 16 + g + rr * 8;
+    if (r < R) {
+      float* op = dpos + (size_t)r * a.d + h * DK;
+#pragma unroll
+      for (int nt = 0; nt < DK / 8; ++nt) {
+        op[nt * 8 + 2 * c] += acc[nt][rr * 2];
+        op[nt * 8 + 2 * c + 1] += acc[nt][rr * 2 + 1];
+      }
+    }
+  }
+}
+
+static int fill_args(AttnArgs& a, const void* qkv, const void* pos, const float* bu, const float* bv,
+                     const int32_t* lengths, int B, int T, int h, int dk, float drop_p, unsigned long long seed,
+                     unsigned int site) {
+  B2C_REQUIRE(dk == 64 || dk == 128, "relpos_attn: head dim %d not built (64, 128)", dk);
+  B2C_REQUIRE(B > 0 && T > 0 && h > 0, "relpos_attn: bad shape");
+  a.qkv = reinterpret_cast<const bf16*>(qkv);
+  a.pos = reinterpret_cast<const bf16*>(pos);
+  a.bias_u = bu; a.bias_v = bv; a.lengths = lengths;
+  a.B = B; a.T = T; a.H = h; a.d = h * dk;
+  a.scale = 1.0f / sqrtf((float)dk);
+  a.drop_p = drop_p; a.seed = seed; a.site = site;
+  a.drop_keep = 0; a.drop_scale = 1.f;
+  if (drop_p > 0.f) {
+    a.drop_keep = (unsigned int)((1.0 - (double)drop_p) * 4294967296.0);
+    a.drop_scale = 1.f / (1.f - drop_p);
+  }
+  return B2C_OK;
+}
+
+template <int DK>
+static size_t smem_q() { return (size_t)(64 + 64 + 128) * (DK + 8) * 2 + 4 * 16 * SCR_PITCH * 4; }
+
+template <int DK>
+static int launch_fwd(const AttnArgs& a, bf16* ctx, float* lse, cudaStream_t st) {
+  const size_t smem = smem_q<DK>();
+  static bool set = false;
+  if (!set) {
+    B2C_CUDA(cudaFuncSetAttribute(relpos_attn_fwd_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set = true;
+  }
+  relpos_attn_fwd_kernel<DK><<<dim3((a.T + BQ - 1) / BQ, a.H, a.B), 128, smem, st>>>(a, ctx, lse);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+template <int DK>
+static int launch_bwd(const AttnArgs& a, const bf16* ctx, const bf16* dctx, const float* lse, bf16* dqkv, float* dpos,
+                      float* dbu, float* dbv, bf16* ws_ds, bf16* ws_p, int Tp, cudaStream_t st) {
+  const size_t smem1 = smem_q<DK>();
+  const size_t smem2 = (size_t)2 * 64 * (DK + 8) * 2 + (size_t)2 * 64 * (BKV + 8) * 2;
+  const size_t smem3 = (size_t)64 * (DK + 8) * 2 + (size_t)64 * 72 * 2;
+  static bool set = false;
+  if (!set) {
+    B2C_CUDA(cudaFuncSetAttribute(relpos_attn_bwd_q_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    B2C_CUDA(cudaFuncSetAttribute(relpos_attn_bwd_kv_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    B2C_CUDA(cudaFuncSetAttribute(relpos_attn_bwd_pos_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+    set = true;
+  }
+  const int qt = (a.T + BQ - 1) / BQ;
+  relpos_attn_bwd_q_kernel<DK><<<dim3(qt, a.H, a.B), 128, smem1, st>>>(a, ctx, dctx, lse, dqkv, dbu, dbv, ws_ds, ws_p, Tp);
+  B2C_LAUNCH_CHECK();
+  relpos_attn_bwd_kv_kernel<DK><<<dim3(qt, a.H, a.B), 128, smem2, st>>>(a, dctx, ws_ds, ws_p, dqkv, Tp);
+  B2C_LAUNCH_CHECK();
+  relpos_attn_bwd_pos_kernel<DK><<<dim3((2 * a.T - 1 + 63) / 64, a.H), 128, smem3, st>>>(a, ws_ds, dpos, Tp);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+}  // namespace b2c
+
+using namespace b2c;
+
+extern "C" int b2c_relpos_attn_fwd(const void* qkv, const void* pos, const float* bias_u, const float* bias_v,
+                                   const int32_t* lengths, void* ctx, float* lse, int B, int T, int h, int dk,
+                                   float drop_p, unsigned long long seed, unsigned int site, void* stream) {
+  AttnArgs a;
+  int rc = fill_args(a, qkv, pos, bias_u, bias_v, lengths, B, T, h, dk, drop_p, seed, site);
+  if (rc) return rc;
+  if (dk == 64) return launch_fwd<64>(a, reinterpret_cast<bf16*>(ctx), lse, (cudaStream_t)stream);
+  return launch_fwd<128>(a, reinterpret_cast<bf16*>(ctx), lse, (cudaStream_t)stream);
+}
+
+/* workspace: 2 * B*h*T*Tp bf16 with Tp = (T+7)&~7 */
+extern "C" size_t b2c_relpos_attn_bwd_workspace(int B, int T, int h) {
+  const size_t Tp = (size_t)((T + 7) & ~7);
+  return 2 * (size_t)B * h * T * Tp * 2;
+}
+
+extern "C" int b2c_relpos_attn_bwd(const void* qkv, const void* pos, const float* bias_u, const float* bias_v,
+                                   const int32_t* lengths, const void* ctx, const void* dctx, const float* lse,
+                                   void* dqkv, float* dpos_f32, float* dbias_u, float* dbias_v, void* workspace,
+                                   size_t workspace_bytes, int B, int T, int h, int dk, float drop_p,
+                                   unsigned long long seed, unsigned int site, void* stream) {
+  AttnArgs a;
+  int rc = fill_args(a, qkv, pos, bias_u, bias_v, lengths, B, T, h, dk, drop_p, seed, site);
+  if (rc) return rc;
+  const int Tp = (T + 7) & ~7;
+  B2C_REQUIRE(workspace && workspace_bytes >= b2c_relpos_attn_bwd_workspace(B, T, h), "relpos_attn_bwd: workspace too small");
+  bf16* ws_ds = reinterpret_cast<bf16*>(workspace);
+  bf16* ws_p = ws_ds + (size_t)B * h * T * Tp;
+  if (dk == 64)
+    return launch_bwd<64>(a, reinterpret_cast<const bf16*>(ctx), reinterpret_cast<const bf16*>(dctx), lse,
+                          reinterpret_cast<bf16*>(dqkv), dpos_f32, dbias_u, dbias_v, ws_ds, ws_p, Tp, (cudaStream_t)stream);
+  return launch_bwd<128>(a, reinterpret_cast<const bf16*>(ctx), reinterpret_cast<const bf16*>(dctx), lse,
+                         reinterpret_cast<bf16*>(dqkv), dpos_f32, dbias_u, dbias_v, ws_ds, ws_p, Tp, (cudaStream_t)stream);
+}

@@ -1,0 +1,385 @@
+// K6: ConformerConvolution core between the two pointwise GEMMs (conformer_modules.py:320-350):
+//   depthwise k-tap conv over time (CausalConv1D with symmetric padding, causal_convs.py:130-150) + bias,
+//   BatchNorm1d (train: batch statistics over all B*T frames incl. padded ones; eval: running stats), SiLU,
+//   and their backward passes.  Channels-last [B*T, d] bf16 tiles staged in shared memory with a (k-1) halo,
+//   two channels per thread (bf16x2), per-thread register accumulators, one atomic per channel per CTA.
+#include "common.cuh"
+
+namespace b2c {
+
+constexpr int kTT = 32;         // output time steps per tile
+constexpr int kCh = 256;        // channels per CTA (128 threads x 2)
+constexpr int kMaxTaps = 31;
+
+// ------------------------------------------------------------------------------------------- forward
+template <int K>
+__global__ void __launch_bounds__(128)
+dwconv_fwd_kernel(const bf16* __restrict__ u, const float* __restrict__ w, const float* __restrict__ bias,
+                  bf16* __restrict__ c, float* __restrict__ bn_sum, float* __restrict__ bn_sumsq, int T, int d,
+                  int tiles_per_cta) {
+  extern __shared__ uint32_t su[];  // [(kTT + K - 1)][128] bf16x2
+  constexpr int PAD = (K - 1) / 2;
+  const int b = blockIdx.z;
+  const int ch = blockIdx.x * kCh + threadIdx.x * 2;
+  const bool act = ch < d;
+  float w0[K], w1[K];
+  float b0 = 0.f, b1 = 0.f;
+  if (act) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      w0[j] = w[(size_t)ch * K + j];
+      w1[j] = w[(size_t)(ch + 1) * K + j];
+    }
+    b0 = bias ? bias[ch] : 0.f;
+    b1 = bias ? bias[ch + 1] : 0.f;
+  }
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  const bf16* ub = u + (size_t)b * T * d;
+  bf16* cb = c + (size_t)b * T * d;
+  for (int tile = 0; tile < tiles_per_cta; ++tile) {
+    const int t0 = (blockIdx.y * tiles_per_cta + tile) * kTT;
+    if (t0 >= T) break;
+    __syncthreads();
+    for (int r = 0; r < kTT + K - 1; ++r) {
+      const int t = t0 + r - PAD;
+      uint32_t v = 0u;
+      if (act && t >= 0 && t < T) v = *reinterpret_cast<const uint32_t*>(ub + (size_t)t * d + ch);
+      su[r * 128 + threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (act) {
+      const int nt = min(kTT, T - t0);
+      for (int i = 0; i < nt; ++i) {
+        float a0 = b0, a1 = b1;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const float2 x = unpack_bf16(su[(i + j) * 128 + threadIdx.x]);
+          a0 = fmaf(w0[j], x.x, a0);
+          a1 = fmaf(w1[j], x.y, a1);
+        }
+        const uint32_t packed = pack_bf16(a0, a1);
+        *reinterpret_cast<uint32_t*>(cb + (size_t)(t0 + i) * d + ch) = packed;
+        const float2 r = unpack_bf16(packed);  // BatchNorm sees the bf16 conv output
+        s0 += r.x; s1 += r.y; q0 += r.x * r.x; q1 += r.y * r.y;
+      }
+    }
+  }
+  if (act && bn_sum) {
+    atomicAdd(bn_sum + ch, s0); atomicAdd(bn_sum + ch + 1, s1);
+    atomicAdd(bn_sumsq + ch, q0); atomicAdd(bn_sumsq + ch + 1, q1);
+  }
+}
+
+__global__ void bn_finalize_kernel(const float* __restrict__ bn_sum, const float* __restrict__ bn_sumsq,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ rstd_out, float count, int d, int training, float momentum,
+                                   float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  float mean, var;
+  if (training) {
+    mean = bn_sum[c] / count;
+    var = fmaxf(bn_sumsq[c] / count - mean * mean, 0.f);  // biased variance normalises (nn.BatchNorm1d)
+    if (running_mean) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+    }
+  } else {
+    mean = running_mean[c];
+    var = running_var[c];
+  }
+  const float rstd = rsqrtf(var + eps);
+  const float sc = gamma[c] * rstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - mean * sc;
+  if (mean_out) mean_out[c] = mean;
+  if (rstd_out) rstd_out[c] = rstd;
+}
+
+// s = bf16(silu(bf16(c*scale + shift)))   [M, d], d even
+__global__ void __launch_bounds__(256)
+bn_silu_fwd_kernel(const bf16* __restrict__ c, const float* __restrict__ scale, const float* __restrict__ shift,
+                   bf16* __restrict__ s, long long total_pairs, int d) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_pairs) return;
+  const int ch = (int)((i * 2) % d);
+  const float2 x = unpack_bf16(reinterpret_cast<const uint32_t*>(c)[i]);
+  const float n0 = bf16_round(fmaf(x.x, scale[ch], shift[ch]));
+  const float n1 = bf16_round(fmaf(x.y, scale[ch + 1], shift[ch + 1]));
+  reinterpret_cast<uint32_t*>(s)[i] = pack_bf16(silu_f(n0), silu_f(n1));
+}
+
+// ------------------------------------------------------------------------------------------- backward
+// phase 1: per-channel sum(dz), sum(dz*xhat) with dz = ds * silu'(bn), bn = bf16(c*scale+shift)
+__global__ void __launch_bounds__(128)
+bn_silu_bwd_reduce_kernel(const bf16* __restrict__ ds, const bf16* __restrict__ c, const float* __restrict__ scale,
+                          const float* __restrict__ shift, const float* __restrict__ mean, const float* __restrict__ rstd,
+                          float* __restrict__ sum_dz, float* __restrict__ sum_dz_xhat, long long M, int d,
+                          int rows_per_cta) {
+  const int ch = blockIdx.x * kCh + threadIdx.x * 2;
+  if (ch >= d) return;
+  const float sc0 = scale[ch], sc1 = scale[ch + 1], sh0 = shift[ch], sh1 = shift[ch + 1];
+  const float m0 = mean[ch], m1 = mean[ch + 1], r0 = rstd[ch], r1 = rstd[ch + 1];
+  const long long row0 = (long long)blockIdx.y * rows_per_cta;
+  const long long row1 = min(M, row0 + rows_per_cta);
+  float a0 = 0.f, a1 = 0.f, x0 = 0.f, x1 = 0.f;
+  for (long long r = row0; r < row1; ++r) {
+    const float2 cv = unpack_bf16(*reinterpret_cast<const uint32_t*>(c + r * d + ch));
+    const float2 dv = unpack_bf16(*reinterpret_cast<const uint32_t*>(ds + r * d + ch));
+    const float n0 = bf16_round(fmaf(cv.x, sc0, sh0)), n1 = bf16_round(fmaf(cv.y, sc1, sh1));
+    const float dz0 = dv.x * dsilu_f(n0), dz1 = dv.y * dsilu_f(n1);
+    a0 += dz0; a1 += dz1;
+    x0 += dz0 * (cv.x - m0) * r0;
+    x1 += dz1 * (cv.y - m1) * r1;
+  }
+  atomicAdd(sum_dz + ch, a0); atomicAdd(sum_dz + ch + 1, a1);
+  atomicAdd(sum_dz_xhat + ch, x0); atomicAdd(sum_dz_xhat + ch + 1, x1);
+}
+
+// phase 2: dc = gamma*rstd*(dz - mean(dz) - xhat*mean(dz*xhat)) (train) | gamma*rstd*dz (eval)
+__global__ void __launch_bounds__(256)
+bn_silu_bwd_apply_kernel(const bf16* __restrict__ ds, const bf16* __restrict__ c, const float* __restrict__ gamma,
+                         const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                         const float* __restrict__ rstd, const float* __restrict__ sum_dz,
+                         const float* __restrict__ sum_dz_xhat, bf16* __restrict__ dc, float* __restrict__ dgamma,
+                         float* __restrict__ dbeta, long long total_pairs, int d, float inv_count, int training) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < d && dgamma) {  // parameter gradients once (first d threads of the grid)
+    atomicAdd(dgamma + i, sum_dz_xhat[i]);
+    atomicAdd(dbeta + i, sum_dz[i]);
+  }
+  if (i >= total_pairs) return;
+  const int ch = (int)((i * 2) % d);
+  const float2 cv = unpack_bf16(reinterpret_cast<const uint32_t*>(c)[i]);
+  const float2 dv = unpack_bf16(reinterpret_cast<const uint32_t*>(ds)[i]);
+  float o[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int cc = ch + k;
+    const float cval = k ? cv.y : cv.x, dval = k ? dv.y : dv.x;
+    const float n = bf16_round(fmaf(cval, scale[cc], shift[cc]));
+    const float dz = dval * dsilu_f(n);
+    const float gr = gamma[cc] * rstd[cc];
+    if (training) {
+      const float xhat = (cval - mean[cc]) * rstd[cc];
+      o[k] = gr * (dz - sum_dz[cc] * inv_count - xhat * sum_dz_xhat[cc] * inv_count);
+    } else {
+      o[k] = gr * dz;
+    }
+  }
+  reinterpret_cast<uint32_t*>(dc)[i] = pack_bf16(o[0], o[1]);
+}
+
+// du[t] = mask(t) * sum_j w[j] * dc[t + PAD - j];  dw[j] += sum_t dc[t] * u[t + j - PAD];  dbias += sum_t dc[t]
+template <int K>
+__global__ void __launch_bounds__(128)
+dwconv_bwd_kernel(const bf16* __restrict__ dc, const bf16* __restrict__ u, const float* __restrict__ w,
+                  const int32_t* __restrict__ lengths, bf16* __restrict__ du, float* __restrict__ dw,
+                  float* __restrict__ dbias, int T, int d, int tiles_per_cta) {
+  extern __shared__ uint32_t sm[];
+  constexpr int PAD = (K - 1) / 2;
+  constexpr int ROWS = kTT + K - 1;
+  uint32_t* sdc = sm;               // [ROWS][128]
+  uint32_t* suu = sm + ROWS * 128;  // [ROWS][128]
+  const int b = blockIdx.z;
+  const int ch = blockIdx.x * kCh + threadIdx.x * 2;
+  const bool act = ch < d;
+  const int len = lengths ? lengths[b] : T;
+  float w0[K], w1[K], g0[K], g1[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    w0[j] = act ? w[(size_t)ch * K + j] : 0.f;
+    w1[j] = act ? w[(size_t)(ch + 1) * K + j] : 0.f;
+    g0[j] = g1[j] = 0.f;
+  }
+  float db0 = 0.f, db1 = 0.f;
+  const bf16* dcb = dc + (size_t)b * T * d;
+  const bf16* ub = u + (size_t)b * T * d;
+  bf16* dub = du + (size_t)b * T * d;
+  for (int tile = 0; tile < tiles_per_cta; ++tile) {
+    const int t0 = (blockIdx.y * tiles_per_cta + tile) * kTT;
+    if (t0 >= T) break;
+    __syncthreads();
+    for (int r = 0; r < ROWS; ++r) {
+      const int t = t0 + r - PAD;
+      uint32_t a = 0u, bb = 0u;
+      if (act && t >= 0 && t < T) {
+        a = *reinterpret_cast<const uint32_t*>(dcb + (size_t)t * d + ch);
+        bb = *reinterpret_cast<const uint32_t*>(ub + (size_t)t * d + ch);
+      }
+      sdc[r * 128 + threadIdx.x] = a;
+      suu[r * 128 + threadIdx.x] = bb;
+    }
+    __syncthreads();
+    if (act) {
+      const int nt = min(kTT, T - t0);
+      for (int i = 0; i < nt; ++i) {
+        // du[t0+i]: dc index (t0+i) + PAD - j  ↔ smem row i + 2*PAD - j
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const float2 x = unpack_bf16(sdc[(i + 2 * PAD - j) * 128 + threadIdx.x]);
+          a0 = fmaf(w0[j], x.x, a0);
+          a1 = fmaf(w1[j], x.y, a1);
+        }
+        const bool valid = (t0 + i) < len;
+        *reinterpret_cast<uint32_t*>(dub + (size_t)(t0 + i) * d + ch) = valid ? pack_bf16(a0, a1) : 0u;
+        // dw: dc[t0+i] (smem row i+PAD) times u[t0+i+j-PAD] (smem row i+j)
+        const float2 g = unpack_bf16(sdc[(i + PAD) * 128 + threadIdx.x]);
+        db0 += g.x; db1 += g.y;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const float2 x = unpack_bf16(suu[(i + j) * 128 + threadIdx.x]);
+          g0[j] = fmaf(g.x, x.x, g0[j]);
+          g1[j] = fmaf(g.y, x.y, g1[j]);
+        }
+      }
+    }
+  }
+  if (act) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      atomicAdd(dw + (size_t)ch * K + j, g0[j]);
+      atomicAdd(dw + (size_t)(ch + 1) * K + j, g1[j]);
+    }
+    if (dbias) { atomicAdd(dbias + ch, db0); atomicAdd(dbias + ch + 1, db1); }
+  }
+}
+
+// interleaved (value, gate): dg[2j] = du*sig(g); dg[2j+1] = du*a*sig(g)*(1-sig(g))
+__global__ void __launch_bounds__(256)
+glu_bwd_kernel(const bf16* __restrict__ du, const bf16* __restrict__ g, bf16* __restrict__ dg, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // index into du [M*d]
+  if (i >= total) return;
+  const float dv = __bfloat162float(du[i]);
+  const float2 ag = unpack_bf16(reinterpret_cast<const uint32_t*>(g)[i]);
+  const float s = sigmoid_f(ag.y);
+  reinterpret_cast<uint32_t*>(dg)[i] = pack_bf16(dv * s, dv * ag.x * s * (1.f - s));
+}
+
+template <int K>
+static int launch_dw_fwd(const bf16* u, const float* w, const float* bias, bf16* c, float* s, float* q, int B, int T,
+                         int d, cudaStream_t st) {
+  const int tiles = (T + kTT - 1) / kTT;
+  int tpc = 1;
+  const int cb = (d + kCh - 1) / kCh;
+  while ((long long)cb * ((tiles + tpc - 1) / tpc) * B > (long long)num_sms() * 8 && tpc < tiles) ++tpc;
+  const size_t smem = (size_t)(kTT + K - 1) * 128 * 4;
+  dwconv_fwd_kernel<K><<<dim3(cb, (tiles + tpc - 1) / tpc, B), 128, smem, st>>>(u, w, bias, c, s, q, T, d, tpc);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+template <int K>
+static int launch_dw_bwd(const bf16* dc, const bf16* u, const float* w, const int32_t* len, bf16* du, float* dw,
+                         float* db, int B, int T, int d, cudaStream_t st) {
+  const int tiles = (T + kTT - 1) / kTT;
+  const int cb = (d + kCh - 1) / kCh;
+  int tpc = 1;
+  while ((long long)cb * ((tiles + tpc - 1) / tpc) * B > (long long)num_sms() * 4 && tpc < tiles) ++tpc;
+  const size_t smem = (size_t)(kTT + K - 1) * 128 * 4 * 2;
+  static bool set = false;
+  if (!set) {
+    B2C_CUDA(cudaFuncSetAttribute(dwconv_bwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    set = true;
+  }
+  dwconv_bwd_kernel<K><<<dim3(cb, (tiles + tpc - 1) / tpc, B), 128, smem, st>>>(dc, u, w, len, du, dw, db, T, d, tpc);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+}  // namespace b2c
+
+using namespace b2c;
+
+extern "C" int b2c_dwconv_fwd(const void* u_bf16, const float* w, const float* bias, void* c_bf16, float* bn_sum,
+                              float* bn_sumsq, int B, int T, int d, int k, void* stream) {
+  B2C_REQUIRE(d % 2 == 0 && B > 0 && T > 0, "dwconv_fwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bf16* u = reinterpret_cast<const bf16*>(u_bf16);
+  bf16* c = reinterpret_cast<bf16*>(c_bf16);
+  switch (k) {
+    case 31: return launch_dw_fwd<31>(u, w, bias, c, bn_sum, bn_sumsq, B, T, d, st);
+    case 9: return launch_dw_fwd<9>(u, w, bias, c, bn_sum, bn_sumsq, B, T, d, st);
+    case 5: return launch_dw_fwd<5>(u, w, bias, c, bn_sum, bn_sumsq, B, T, d, st);
+  }
+  set_last_error("dwconv_fwd: kernel size %d not built (31, 9, 5)", k);
+  return B2C_ERR_UNSUPPORTED;
+}
+
+extern "C" int b2c_bn_finalize(const float* bn_sum, const float* bn_sumsq, const float* gamma, const float* beta,
+                               float* running_mean, float* running_var, float* scale, float* shift, float* mean_out,
+                               float* rstd_out, long long count, int d, int training, float momentum, float eps,
+                               void* stream) {
+  bn_finalize_kernel<<<(d + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bn_sum, bn_sumsq, gamma, beta, running_mean,
+                                                                       running_var, scale, shift, mean_out, rstd_out,
+                                                                       (float)count, d, training, momentum, eps);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_bn_silu_fwd(const void* c_bf16, const float* scale, const float* shift, void* s_bf16, long long M,
+                               int d, void* stream) {
+  B2C_REQUIRE(d % 2 == 0, "bn_silu: d odd");
+  const long long pairs = M * d / 2;
+  bn_silu_fwd_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(c_bf16), scale, shift, reinterpret_cast<bf16*>(s_bf16), pairs, d);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_bn_silu_bwd_reduce(const void* ds_bf16, const void* c_bf16, const float* scale, const float* shift,
+                                      const float* mean, const float* rstd, float* sum_dz, float* sum_dz_xhat,
+                                      long long M, int d, void* stream) {
+  const int cb = (d + kCh - 1) / kCh;
+  int row_blocks = (num_sms() * 8 + cb - 1) / cb;
+  int rows_per_cta = (int)((M + row_blocks - 1) / row_blocks);
+  if (rows_per_cta < 32) rows_per_cta = 32;
+  row_blocks = (int)((M + rows_per_cta - 1) / rows_per_cta);
+  bn_silu_bwd_reduce_kernel<<<dim3(cb, row_blocks), 128, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(ds_bf16), reinterpret_cast<const bf16*>(c_bf16), scale, shift, mean, rstd, sum_dz,
+      sum_dz_xhat, M, d, rows_per_cta);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_bn_silu_bwd_apply(const void* ds_bf16, const void* c_bf16, const float* gamma, const float* scale,
+                                     const float* shift, const float* mean, const float* rstd, const float* sum_dz,
+                                     const float* sum_dz_xhat, void* dc_bf16, float* dgamma, float* dbeta, long long M,
+                                     int d, int training, void* stream) {
+  const long long pairs = M * d / 2;
+  B2C_REQUIRE(pairs >= d, "bn_silu_bwd_apply: tensor smaller than d");
+  bn_silu_bwd_apply_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(ds_bf16), reinterpret_cast<const bf16*>(c_bf16), gamma, scale, shift, mean, rstd,
+      sum_dz, sum_dz_xhat, reinterpret_cast<bf16*>(dc_bf16), dgamma, dbeta, pairs, d, 1.0f / (float)M, training);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_dwconv_bwd(const void* dc_bf16, const void* u_bf16, const float* w, const int32_t* lengths,
+                              void* du_bf16, float* dw, float* dbias, int B, int T, int d, int k, void* stream) {
+  B2C_REQUIRE(d % 2 == 0 && B > 0 && T > 0, "dwconv_bwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bf16* dc = reinterpret_cast<const bf16*>(dc_bf16);
+  const bf16* u = reinterpret_cast<const bf16*>(u_bf16);
+  bf16* du = reinterpret_cast<bf16*>(du_bf16);
+  switch (k) {
+    case 31: return launch_dw_bwd<31>(dc, u, w, lengths, du, dw, dbias, B, T, d, st);
+    case 9: return launch_dw_bwd<9>(dc, u, w, lengths, du, dw, dbias, B, T, d, st);
+    case 5: return launch_dw_bwd<5>(dc, u, w, lengths, du, dw, dbias, B, T, d, st);
+  }
+  set_last_error("dwconv_bwd: kernel size %d not built (31, 9, 5)", k);
+  return B2C_ERR_UNSUPPORTED;
+}
+
+extern "C" int b2c_glu_bwd(const void* du_bf16, const void* g_bf16, void* dg_bf16, long long M, int d, void* stream) {
+  const long long total = M * d;
+  glu_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(du_bf16), reinterpret_cast<const bf16*>(g_bf16), reinterpret_cast<bf16*>(dg_bf16),
+      total);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}

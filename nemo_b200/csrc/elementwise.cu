@@ -1,0 +1,379 @@
+// HBM-bound row/column kernels of the Conformer block: LayerNorm fwd/bwd (+ residual-gradient fan-in, dropout of the
+// outgoing branch gradient), bias-gradient column sums, fp32→bf16 weight casts / permutes, rel-pos table, lengths.
+// One warp per row, 128-bit loads, warp-shuffle reductions.  Reference: torch.nn.LayerNorm(d) x5 per ConformerLayer
+// (conformer_modules.py:94,98,108,154,158) under bf16 autocast (fp32 maths, bf16 consumer).
+#include "common.cuh"
+
+namespace b2c {
+
+constexpr int kMaxVec = 8;  // d <= 1024 (8 float4 per lane)
+
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     bf16* __restrict__ y16, float* __restrict__ y32, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, int M, int d) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int nv = d >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * d);
+  float4 v[kMaxVec];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = i * 32 + lane;
+    v[i] = (c < nv) ? xr[c] : make_float4(0, 0, 0, 0);
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) / (float)d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nv) {
+      float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, dd = v[i].w - mean;
+      q += a * a + b * b + cc * cc + dd * dd;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)d + 1e-5f);
+  if (lane == 0) {
+    if (mean_out) mean_out[warp] = mean;
+    if (rstd_out) rstd_out[warp] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nv) {
+      const float4 g = reinterpret_cast<const float4*>(gamma)[c];
+      const float4 bt = reinterpret_cast<const float4*>(beta)[c];
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + bt.x;
+      o.y = (v[i].y - mean) * rstd * g.y + bt.y;
+      o.z = (v[i].z - mean) * rstd * g.z + bt.z;
+      o.w = (v[i].w - mean) * rstd * g.w + bt.w;
+      if (y32) reinterpret_cast<float4*>(y32 + (size_t)warp * d)[c] = o;
+      if (y16) reinterpret_cast<uint2*>(y16 + (size_t)warp * d)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+    }
+  }
+}
+
+struct DropArgs {
+  unsigned long long seed;
+  unsigned int site, keep;
+  float scale;
+};
+
+// rows handled per warp are strided so each warp keeps per-column dgamma/dbeta partials in registers
+template <bool DY_BF16>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dr,
+                     int accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta, bf16* __restrict__ next16,
+                     float next_scale, DropArgs drop, int M, int d) {
+  extern __shared__ float red[];  // [2][d] CTA partials
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int nv = d >> 2;
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float4 ag[kMaxVec], ab[kMaxVec];
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) ag[i] = ab[i] = make_float4(0, 0, 0, 0);
+  float4 g[kMaxVec];
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = i * 32 + lane;
+    g[i] = (c < nv) ? reinterpret_cast<const float4*>(gamma)[c] : make_float4(0, 0, 0, 0);
+  }
+  for (int row = blockIdx.x * wpb + wib; row < M; row += gridDim.x * wpb) {
+    const float mu = mean[row], rs = rstd[row];
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d);
+    float4 xh[kMaxVec], dyv[kMaxVec];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int c = i * 32 + lane;
+      if (c < nv) {
+        float4 xv = xr[c];
+        float4 dv;
+        if (DY_BF16) {
+          uint2 u = reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy_) + (size_t)row * d)[c];
+          float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+          dv = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+          dv = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (size_t)row * d)[c];
+        }
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        dyv[i] = dv;
+        ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
+        ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
+        const float a0 = dv.x * g[i].x, a1 = dv.y * g[i].y, a2 = dv.z * g[i].z, a3 = dv.w * g[i].w;
+        s1 += a0 + a1 + a2 + a3;
+        s2 += a0 * xh[i].x + a1 * xh[i].y + a2 * xh[i].z + a3 * xh[i].w;
+      } else {
+        xh[i] = dyv[i] = make_float4(0, 0, 0, 0);
+      }
+    }
+    s1 = warp_sum(s1) / (float)d;
+    s2 = warp_sum(s2) / (float)d;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int c = i * 32 + lane;
+      if (c < nv) {
+        float4 o;
+        o.x = rs * (dyv[i].x * g[i].x - s1 - xh[i].x * s2);
+        o.y = rs * (dyv[i].y * g[i].y - s1 - xh[i].y * s2);
+        o.z = rs * (dyv[i].z * g[i].z - s1 - xh[i].z * s2);
+        o.w = rs * (dyv[i].w * g[i].w - s1 - xh[i].w * s2);
+        float4* drp = reinterpret_cast<float4*>(dr + (size_t)row * d) + c;
+        if (accumulate) {
+          float4 p = *drp;
+          o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
+        }
+        *drp = o;
+        if (next16) {
+          float n0 = o.x * next_scale, n1 = o.y * next_scale, n2 = o.z * next_scale, n3 = o.w * next_scale;
+          if (drop.keep != 0) {
+            const uint64_t idx = (uint64_t)row * (uint64_t)d + (uint64_t)c * 4;
+            n0 = dropout_keep(drop.seed, drop.site, idx, drop.keep) ? n0 * drop.scale : 0.f;
+            n1 = dropout_keep(drop.seed, drop.site, idx + 1, drop.keep) ? n1 * drop.scale : 0.f;
+            n2 = dropout_keep(drop.seed, drop.site, idx + 2, drop.keep) ? n2 * drop.scale : 0.f;
+            n3 = dropout_keep(drop.seed, drop.site, idx + 3, drop.keep) ? n3 * drop.scale : 0.f;
+          }
+          reinterpret_cast<uint2*>(next16 + (size_t)row * d)[c] = make_uint2(pack_bf16(n0, n1), pack_bf16(n2, n3));
+        }
+      }
+    }
+  }
+  // CTA reduction of dgamma/dbeta partials, then one atomic per column per CTA
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nv) {
+      atomicAdd(&red[c * 4 + 0], ag[i].x); atomicAdd(&red[c * 4 + 1], ag[i].y);
+      atomicAdd(&red[c * 4 + 2], ag[i].z); atomicAdd(&red[c * 4 + 3], ag[i].w);
+      atomicAdd(&red[d + c * 4 + 0], ab[i].x); atomicAdd(&red[d + c * 4 + 1], ab[i].y);
+      atomicAdd(&red[d + c * 4 + 2], ab[i].z); atomicAdd(&red[d + c * 4 + 3], ab[i].w);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + i, red[i]);
+    if (dbeta) atomicAdd(dbeta + i, red[d + i]);
+  }
+}
+
+// out[n] += sum_m in[m, n]; CTA = 64 columns x row-chunk
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const bf16* __restrict__ in, float* __restrict__ out, int M, int N, int ld, int rows_per_cta) {
+  __shared__ float red[8][64];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n = blockIdx.x * 64 + lane * 2;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
+  float a = 0.f, b = 0.f;
+  if (n < N) {
+    for (int m = r0 + w; m < r1; m += 8) {
+      if (n + 1 < N) {
+        float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(in + (size_t)m * ld + n));
+        a += v.x; b += v.y;
+      } else {
+        a += __bfloat162float(in[(size_t)m * ld + n]);
+      }
+    }
+  }
+  red[w][lane * 2] = a;
+  red[w][lane * 2 + 1] = b;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+    const int nn = blockIdx.x * 64 + threadIdx.x;
+    if (nn < N) atomicAdd(out + nn, s);
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n, float scale) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 v = *reinterpret_cast<const float4*>(in + i);
+    *reinterpret_cast<uint2*>(out + i) = make_uint2(pack_bf16(v.x * scale, v.y * scale), pack_bf16(v.z * scale, v.w * scale));
+  } else {
+    for (; i < n; ++i) out[i] = __float2bfloat16_rn(in[i] * scale);
+  }
+}
+
+// in [A,B,C] → out; mode 0: out[b][a][c] (swap dims 0,1); mode 1: out[a][c][b] (swap dims 1,2)
+template <typename TO, bool ACCUM>
+__global__ void permute3_kernel(const float* __restrict__ in, TO* __restrict__ out, int A, int B, int C, int mode) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)A * B * C;
+  if (i >= n) return;
+  // i indexes the OUTPUT (coalesced writes)
+  long long src;
+  if (mode == 0) {
+    const int c = (int)(i % C);
+    const int a = (int)((i / C) % A);
+    const int b = (int)(i / ((long long)C * A));
+    src = ((long long)a * B + b) * C + c;
+  } else {
+    const int b = (int)(i % B);
+    const int c = (int)((i / B) % C);
+    const int a = (int)(i / ((long long)B * C));
+    src = ((long long)a * B + b) * C + c;
+  }
+  if constexpr (sizeof(TO) == 2) {
+    out[i] = __float2bfloat16_rn(in[src]);
+  } else {
+    if (ACCUM) out[i] += in[src];
+    else out[i] = in[src];
+  }
+}
+
+__global__ void fill_f32_kernel(float* p, long long n, float v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// rows r = 0..2T-2 ↔ position T-1-r; pe[2i] = sin(pos*div_i), pe[2i+1] = cos(pos*div_i)
+// (multi_head_attention.py:1007-1020: div = exp(-2i * ln(10000)/d) computed in fp32)
+__global__ void relpos_table_kernel(bf16* __restrict__ pe16, float* __restrict__ pe32, int T, int d) {
+  const int r = blockIdx.x;
+  const float pos = (float)(T - 1 - r);
+  for (int i = threadIdx.x; i < d / 2; i += blockDim.x) {
+    const float div = expf((float)(2 * i) * -(9.210340371976184f / (float)d));
+    const float a = pos * div;
+    const float s = sinf(a), c = cosf(a);
+    if (pe16) {
+      pe16[(size_t)r * d + 2 * i] = __float2bfloat16_rn(s);
+      pe16[(size_t)r * d + 2 * i + 1] = __float2bfloat16_rn(c);
+    }
+    if (pe32) {
+      pe32[(size_t)r * d + 2 * i] = s;
+      pe32[(size_t)r * d + 2 * i + 1] = c;
+    }
+  }
+}
+
+// calc_length / calculate_conv_output_size with k=3, s=2, pad 1+1: L → (L + 2 - 3)//2 + 1 (floor), n times
+__global__ void subsample_lengths_kernel(const int64_t* __restrict__ len_in, int32_t* __restrict__ len_in32,
+                                         int32_t* __restrict__ len_stage, int64_t* __restrict__ len_out64, int B,
+                                         int n_convs) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  long long l = len_in[b];
+  if (len_in32) len_in32[b] = (int32_t)l;
+  for (int i = 0; i < n_convs; ++i) {
+    long long num = l + 2 - 3;
+    long long q = num / 2;
+    if (num % 2 != 0 && num < 0) --q;  // floor
+    l = q + 1;
+    if (len_stage) len_stage[i * B + b] = (int32_t)l;
+  }
+  if (len_out64) len_out64[b] = l;
+}
+
+}  // namespace b2c
+
+using namespace b2c;
+
+extern "C" int b2c_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
+                                 float* mean, float* rstd, int M, int d, void* stream) {
+  B2C_REQUIRE(d % 4 == 0 && d <= kMaxVec * 128, "layernorm: d=%d unsupported (need d%%4==0, d<=1024)", d);
+  B2C_REQUIRE(M > 0, "layernorm: M=%d", M);
+  const int wpb = 8;
+  layernorm_fwd_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
+      x, gamma, beta, reinterpret_cast<bf16*>(y_bf16), y_f32, mean, rstd, M, d);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* gamma, const float* mean,
+                                 const float* rstd, float* dr, int accumulate, float* dgamma, float* dbeta,
+                                 void* next_bf16, float next_scale, float drop_p, unsigned long long seed,
+                                 unsigned int site, int M, int d, void* stream) {
+  B2C_REQUIRE(d % 4 == 0 && d <= kMaxVec * 128, "layernorm_bwd: d=%d unsupported", d);
+  DropArgs da{seed, site, 0u, 1.f};
+  if (drop_p > 0.f) {
+    da.keep = (unsigned int)((1.0 - (double)drop_p) * 4294967296.0);
+    da.scale = 1.f / (1.f - drop_p);
+  }
+  const int wpb = 8;
+  int grid = (M + wpb - 1) / wpb;
+  const int cap = num_sms() * 4;
+  if (grid > cap) grid = cap;
+  const size_t smem = 2 * (size_t)d * sizeof(float);
+  if (dy_is_bf16)
+    layernorm_bwd_kernel<true><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(
+        dy, x, gamma, mean, rstd, dr, accumulate, dgamma, dbeta, reinterpret_cast<bf16*>(next_bf16), next_scale, da, M, d);
+  else
+    layernorm_bwd_kernel<false><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(
+        dy, x, gamma, mean, rstd, dr, accumulate, dgamma, dbeta, reinterpret_cast<bf16*>(next_bf16), next_scale, da, M, d);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_colsum_bf16(const void* in_bf16, float* out, int M, int N, int ld, void* stream) {
+  B2C_REQUIRE(M > 0 && N > 0 && ld % 2 == 0, "colsum: bad args");
+  const int col_blocks = (N + 63) / 64;
+  int row_blocks = (num_sms() * 4 + col_blocks - 1) / col_blocks;
+  if (row_blocks < 1) row_blocks = 1;
+  int rows_per_cta = (M + row_blocks - 1) / row_blocks;
+  if (rows_per_cta < 64) rows_per_cta = 64;
+  row_blocks = (M + rows_per_cta - 1) / rows_per_cta;
+  colsum_bf16_kernel<<<dim3(col_blocks, row_blocks), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(in_bf16), out, M, N, ld, rows_per_cta);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_cast_bf16(const float* in, void* out_bf16, long long n, float scale, void* stream) {
+  B2C_REQUIRE(n > 0, "cast: n=%lld", n);
+  const long long threads = (n + 3) / 4;
+  cast_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      in, reinterpret_cast<bf16*>(out_bf16), n, scale);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_permute3_bf16(const float* in, void* out_bf16, int A, int B, int C, int mode, void* stream) {
+  const long long n = (long long)A * B * C;
+  B2C_REQUIRE(n > 0 && (mode == 0 || mode == 1), "permute3: bad args");
+  permute3_kernel<bf16, false><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      in, reinterpret_cast<bf16*>(out_bf16), A, B, C, mode);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_permute3_f32(const float* in, float* out, int A, int B, int C, int mode, int accumulate,
+                                void* stream) {
+  const long long n = (long long)A * B * C;
+  B2C_REQUIRE(n > 0 && (mode == 0 || mode == 1), "permute3: bad args");
+  if (accumulate)
+    permute3_kernel<float, true><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, out, A, B, C, mode);
+  else
+    permute3_kernel<float, false><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, out, A, B, C, mode);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_fill_f32(float* p, long long n, float v, void* stream) {
+  if (n <= 0) return B2C_OK;
+  fill_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, n, v);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_relpos_table(void* pos_bf16, float* pos_f32, int T, int d, void* stream) {
+  B2C_REQUIRE(T > 0 && d % 2 == 0, "relpos_table: bad args");
+  relpos_table_kernel<<<2 * T - 1, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<bf16*>(pos_bf16), pos_f32, T, d);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_subsample_lengths(const int64_t* len_in, int32_t* len_in32, int32_t* len_stage, int64_t* len_out64,
+                                     int B, int n_convs, void* stream) {
+  B2C_REQUIRE(B > 0 && n_convs >= 0, "subsample_lengths: bad args");
+  subsample_lengths_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(len_in, len_in32, len_stage, len_out64, B,
+                                                                             n_convs);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
