@@ -45,7 +45,8 @@ typedef enum {
                             out1[m,n/2] = bf16(a*sigmoid(g)) * (t<len)                (pointwise_conv1+GLU) */
   B2C_EPI_DSILU = 4,     /* out0 = bf16(dropout(bf16(acc)) * silu'(aux(bf16)[m,n]))        (FFN backward)  */
   B2C_EPI_RELU_MASK = 5, /* out0 = bf16(relu(acc+bias)) * (t<len)                      (subsampling conv) */
-  B2C_EPI_ACCUM_F32 = 6  /* out0(f32)[m,n] += alpha*acc  (split-K, atomic)             (weight gradients)  */
+  B2C_EPI_ACCUM_F32 = 6, /* out0(f32)[m,n] += alpha*acc  (split-K, atomic)             (weight gradients)  */
+  B2C_EPI_RELU_BWD = 7   /* out0 = bf16(aux(bf16)[m,n] > 0 ? acc : 0)          (gradient through ReLU+mask) */
 } b2c_epilogue_mode;
 
 typedef struct {
@@ -96,6 +97,9 @@ int b2c_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const floa
 int b2c_colsum_bf16(const void* in_bf16, float* out, int M, int N, int ld, void* stream);
 /* fp32 → bf16 cast with optional scale */
 int b2c_cast_bf16(const float* in, void* out_bf16, long long n, float scale, void* stream);
+/* out_bf16[i] = bf16(scale * dropout_site(in[i]))  (backward of xscale + pre-encoder dropout) */
+int b2c_scale_drop_cast(const float* in, void* out_bf16, long long n, float scale, float drop_p,
+                        unsigned long long seed, unsigned int site, void* stream);
 /* in [A,B,C] f32 → out permuted; mode 0: out[b][a][c]; mode 1: out[a][c][b].  Weight layout preparation
  * (GLU value/gate interleave, conv taps-major, flatten order) and the inverse for their gradients. */
 int b2c_permute3_bf16(const float* in, void* out_bf16, int A, int B, int C, int mode, void* stream);
@@ -144,6 +148,32 @@ int b2c_relpos_attn_bwd(const void* qkv, const void* pos, const float* bias_u, c
                         float* dpos_f32, float* dbias_u, float* dbias_v, void* workspace, size_t workspace_bytes,
                         int B, int T, int h, int dk, float drop_p, unsigned long long seed, unsigned int site,
                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------ subsampling
+ * First Conv2d(1→C, 3x3, stride 2, pad 1) + bias + ReLU + time masks, channels-last output [B, T1, F1, C] bf16
+ * (subsampling.py:217-253,725-753).  mel [B, F, T] f32 (the encoder's input layout), w [C,1,3,3] f32,
+ * len_in / len_out [B] i32 (valid frames before / after this conv). */
+int b2c_subsample_conv1_fwd(const float* mel, const float* w, const float* bias, const int32_t* len_in,
+                            const int32_t* len_out, void* out_bf16, int B, int F, int T, int C, void* stream);
+/* dw [C,9] += , dbias [C] +=  from dout [B,T1,F1,C] bf16 (already ReLU/mask-gated) */
+int b2c_subsample_conv1_bwd(const float* mel, const void* dout_bf16, const int32_t* len_in, float* dw, float* dbias,
+                            int B, int F, int T, int C, void* stream);
+/* Conv2d(C→C, 3x3, stride 2, pad 1) as an implicit GEMM on tcgen05 (9 shifted, strided 4-D TMA tile loads feed one
+ * TMEM accumulator; no im2col): in [B,T1,F1,C] bf16 → out [B,T2,F2,C] bf16 = relu(conv+bias) * (t2 < len_out).
+ * w_bf16 [C_out, 9*C_in] with k = (kh*3+kw)*C_in + ci. */
+int b2c_conv3x3s2_fwd(const void* in_bf16, const void* w_bf16, const float* bias, const int32_t* len_out,
+                      void* out_bf16, int B, int T1, int F1, int C, void* stream);
+/* data gradient: dx [B,T1,F1,C] = relu'(x) * conv_transpose(dy [B,T2,F2,C]); wd_bf16 [C_in, 9*C_out] with
+ * k = (kh*3+kw)*C_out + co.  Four parity-class implicit GEMMs. */
+int b2c_conv3x3s2_bwd_data(const void* dy_bf16, const void* wd_bf16, const void* x_bf16, void* dx_bf16, int B, int T1,
+                           int F1, int C, void* stream);
+/* weight gradient: dw f32 [C_out, 9*C_in] += (tokens are the contraction dimension; both operands gathered by TMA) */
+int b2c_conv3x3s2_bwd_weight(const void* dy_bf16, const void* x_bf16, float* dw, int B, int T1, int F1, int C,
+                             void* stream);
+/* depthwise Conv2d(C, 3x3, s2, p1, groups=C) channels-last + bias, output rows t2 >= len_out zeroed (dw_striding,
+ * subsampling.py:142-215). */
+int b2c_dwconv3x3s2_fwd(const void* in_bf16, const float* w, const float* bias, const int32_t* len_out, void* out_bf16,
+                        int B, int T1, int F1, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ misc
  * relative positional table rows = positions T-1 … -(T-1) (multi_head_attention.py:1007-1020,1056-1100) */

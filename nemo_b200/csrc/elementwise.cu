@@ -201,6 +201,16 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict_
   }
 }
 
+// out_bf16 = bf16(scale * dropout(in)) — gradient entering pre_encode.out (xscale + pre-encoder dropout backward)
+__global__ void scale_drop_cast_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n, float scale,
+                                       DropArgs drop) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = in[i] * scale;
+  if (drop.keep != 0) v = dropout_keep(drop.seed, drop.site, (uint64_t)i, drop.keep) ? v * drop.scale : 0.f;
+  out[i] = __float2bfloat16_rn(v);
+}
+
 // in [A,B,C] → out; mode 0: out[b][a][c] (swap dims 0,1); mode 1: out[a][c][b] (swap dims 1,2)
 template <typename TO, bool ACCUM>
 __global__ void permute3_kernel(const float* __restrict__ in, TO* __restrict__ out, int A, int B, int C, int mode) {
@@ -330,6 +340,20 @@ extern "C" int b2c_cast_bf16(const float* in, void* out_bf16, long long n, float
   const long long threads = (n + 3) / 4;
   cast_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       in, reinterpret_cast<bf16*>(out_bf16), n, scale);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_scale_drop_cast(const float* in, void* out_bf16, long long n, float scale, float drop_p,
+                                   unsigned long long seed, unsigned int site, void* stream) {
+  B2C_REQUIRE(n > 0, "scale_drop_cast: n=%lld", n);
+  DropArgs da{seed, site, 0u, 1.f};
+  if (drop_p > 0.f) {
+    da.keep = (unsigned int)((1.0 - (double)drop_p) * 4294967296.0);
+    da.scale = 1.f / (1.f - drop_p);
+  }
+  scale_drop_cast_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      in, reinterpret_cast<bf16*>(out_bf16), n, scale, da);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
 }

@@ -26,11 +26,24 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kNumThreads = 256;
 
+// Implicit-GEMM geometry of the 3x3 stride-2 subsampling convolution (no im2col is ever materialised: the
+// A tiles are gathered by 4-D TMA boxes, strided for the forward / weight-gradient, shifted for the data-gradient).
+struct ConvGeom {
+  int C;                // channels per tap (K per tap)
+  int Fq, TR, Tq;       // f positions per time row, time rows per tile (M tile, or K block for wgrad), time rows
+  int tiles_per_batch;  // ceil(Tq / TR)
+  int a_t_mul;          // A time coordinate = t0 * a_t_mul + tap_t
+  int ntaps;
+  int tap_t[9], tap_f[9], tap_k[9];  // A coordinate offsets and B k-offset (elements) per tap
+  int To, Fo, ts, fs, pt, pf;        // output row = ((b*To + t*ts + pt) * Fo + f*fs + pf)
+};
+
 struct GemmParams {
   int M, N, K;
-  int splits;       // split-K factor (fp32 atomic accumulate epilogue only)
+  int splits;       // split-K factor (fp32 atomic accumulate epilogue only); conv wgrad: tap index
   int k_per_split;  // in units of BK blocks
   b2c_epilogue epi;
+  ConvGeom cv;
 };
 
 template <int BN>
@@ -207,6 +220,27 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
     } else {
       for (int j = 0; j < 32 && n0 + j < N; ++j) o[j] = __float2bfloat16_rn(v[j]);
     }
+  } else if (MODE == B2C_EPI_RELU_BWD) {
+    // out_bf16 = (aux_bf16[m,n] > 0) ? acc : 0     (gradient through ReLU + time mask: masked outputs are 0)
+    bf16* o = reinterpret_cast<bf16*>(e.out0) + (size_t)m * ldo + n0;
+    const bf16* y = reinterpret_cast<const bf16*>(e.aux) + (size_t)m * ldo + n0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        const uint4 yy = *reinterpret_cast<const uint4*>(y + j);
+        const uint32_t yw[4] = {yy.x, yy.y, yy.z, yy.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 g = unpack_bf16(yw[q]);
+          ow[q] = pack_bf16(g.x > 0.f ? v[j + 2 * q] : 0.f, g.y > 0.f ? v[j + 2 * q + 1] : 0.f);
+        }
+        *reinterpret_cast<uint4*>(o + j) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+    } else {
+      for (int j = 0; j < 32 && n0 + j < N; ++j)
+        o[j] = __float2bfloat16_rn(__bfloat162float(y[j]) > 0.f ? v[j] : 0.f);
+    }
   } else if (MODE == B2C_EPI_ACCUM_F32) {
     // out_f32[m,n] += alpha * acc  (weight gradients; atomic when split-K)
     float* o = reinterpret_cast<float*>(e.out0) + (size_t)m * ldo + n0;
@@ -226,7 +260,9 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
 }
 
 // ---------------------------------------------------------------- kernel
-template <int BN, int A_MN, int B_MN, int MODE>
+// CONV: 0 = plain GEMM; 1 = conv forward (strided gather A); 2 = conv data-gradient (shifted gather A, scatter rows);
+//       3 = conv weight-gradient (tokens are the contraction; A = dY, B = strided gather of X, one tap per `split`)
+template <int BN, int A_MN, int B_MN, int MODE, int CONV = 0>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using L = SmemLayout<BN>;
@@ -240,9 +276,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+  const int m_tiles = (CONV == 1 || CONV == 2) ? p.M : (p.M + BM - 1) / BM;  // conv fwd/dgrad: p.M = #row tiles
+  const int n_tiles = (p.N + BN - 1) / BN;
   const int total_tiles = m_tiles * n_tiles * p.splits;
-  const int kb_total = (p.K + BK - 1) / BK;
+  const int kb_total = (CONV != 0) ? p.K : (p.K + BK - 1) / BK;               // conv: p.K = #k-blocks
+  // bytes one stage receives (partial boxes of the conv gathers deliver fewer rows than the slot holds)
+  const uint32_t stage_tx = (CONV == 1 || CONV == 2) ? (uint32_t)(p.cv.TR * p.cv.Fq * BK * 2 + L::kBBytes)
+                            : (CONV == 3)            ? (uint32_t)((BM / 64 + BN / 64) * p.cv.TR * p.cv.Fq * 128)
+                                                     : (uint32_t)L::kStageBytes;
+  if (CONV == 3) {
+    // rows the partial boxes never write must read as zero for the MN-major contraction
+    for (int i = threadIdx.x; i < kStages * L::kStageBytes / 16; i += kNumThreads)
+      reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -272,20 +319,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int split = tile % p.splits;
         const int mn = tile / p.splits;
         const int m0 = (mn / n_tiles) * BM, n0 = (mn % n_tiles) * BN;
-        const int kb0 = split * p.k_per_split;
-        const int kb1 = min(kb_total, kb0 + p.k_per_split);
+        const int kb0 = (CONV == 3) ? 0 : split * p.k_per_split;
+        const int kb1 = (CONV == 3) ? kb_total : min(kb_total, kb0 + p.k_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
-          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          mbar_expect_tx(&full_bar[stage], stage_tx);
+          if (CONV == 1 || CONV == 2) {
+            const int cblks = p.cv.C / BK;
+            const int tap = kb / cblks, c0 = (kb - tap * cblks) * BK;
+            const int mb = mn / n_tiles;
+            const int bb = mb / p.cv.tiles_per_batch, t0 = (mb - bb * p.cv.tiles_per_batch) * p.cv.TR;
+            tma_load_4d(sa, &tmA, &full_bar[stage], c0, p.cv.tap_f[tap], t0 * p.cv.a_t_mul + p.cv.tap_t[tap], bb);
+            tma_load_2d(sb, &tmB, &full_bar[stage], p.cv.tap_k[tap] + c0, n0);
+          } else if (CONV == 3) {
+            const int bb = kb / p.cv.tiles_per_batch, t0 = (kb - bb * p.cv.tiles_per_batch) * p.cv.TR;
+            const int tap = split;  // kh*3 + kw
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_4d(sa + c * (64 * BK * 2), &tmA, &full_bar[stage], m0 + c * 64, 0, t0, bb);
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_4d(sb + c * (64 * BK * 2), &tmB, &full_bar[stage], n0 + c * 64, tap % 3 - 1, 2 * t0 + tap / 3 - 1, bb);
+          } else
           if (A_MN) {
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (64 * BK * 2), &tmA, &full_bar[stage], m0 + c * 64, kb * BK);
           } else {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
           }
-          if (B_MN) {
+          if (CONV != 0) {
+          } else if (B_MN) {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (64 * BK * 2), &tmB, &full_bar[stage], n0 + c * 64, kb * BK);
           } else {
@@ -301,8 +365,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0, phase = 0, as = 0, aphase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int split = tile % p.splits;
-        const int kb0 = split * p.k_per_split;
-        const int kb1 = min(kb_total, kb0 + p.k_per_split);
+        const int kb0 = (CONV == 3) ? 0 : split * p.k_per_split;
+        const int kb1 = (CONV == 3) ? kb_total : min(kb_total, kb0 + p.k_per_split);
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
@@ -332,17 +396,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mn = tile / p.splits;
       const int m0 = (mn / n_tiles) * BM, n0 = (mn % n_tiles) * BN;
-      const int kb0 = (tile % p.splits) * p.k_per_split;
-      const bool has_k = kb0 < kb_total;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const int m = m0 + q * 32 + lane;
+      int m = m0 + q * 32 + lane, m_bound = p.M;
+      b2c_epilogue epi = p.epi;
+      if (CONV == 1 || CONV == 2) {
+        const int mb = mn / n_tiles;
+        const int bb = mb / p.cv.tiles_per_batch, t0 = (mb - bb * p.cv.tiles_per_batch) * p.cv.TR;
+        const int r = q * 32 + lane;
+        const int tl = r / p.cv.Fq, fl = r - tl * p.cv.Fq, t = t0 + tl;
+        m_bound = 0x7fffffff;
+        m = (r < p.cv.TR * p.cv.Fq && t < p.cv.Tq)
+                ? ((bb * p.cv.To + t * p.cv.ts + p.cv.pt) * p.cv.Fo + fl * p.cv.fs + p.cv.pf)
+                : m_bound;
+      } else if (CONV == 3) {
+        epi.out0 = reinterpret_cast<float*>(epi.out0) + (size_t)(tile % p.splits) * p.cv.C;  // tap-major columns
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t acc[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), acc);
         tmem_ld_wait();
-        if (has_k) epilogue_row<MODE>(p.epi, m, n0 + c * 32, p.M, p.N, acc, p.splits > 1);
+        epilogue_row<MODE>(epi, m, n0 + c * 32, m_bound, p.N, acc, CONV == 0 && p.splits > 1);
       }
       tc_fence_before();
       __syncwarp();
@@ -388,16 +463,16 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, const bf16* __restr
 // ---------------------------------------------------------------- host launch
 static int g_gemm_impl = -1;  // 0 = tcgen05, 1 = simt (debug)
 
-template <int BN, int A_MN, int B_MN, int MODE>
+template <int BN, int A_MN, int B_MN, int MODE, int CONV = 0>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout<BN>;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, MODE>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, MODE, CONV>;
   static bool attr_set = false;
   if (!attr_set) {
     B2C_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
-  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+  const int m_tiles = (CONV == 1 || CONV == 2) ? p.M : (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
   const int total = m_tiles * n_tiles * p.splits;
   const int grid = total < num_sms() ? total : num_sms();
   kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, p);
@@ -475,6 +550,7 @@ int gemm(const void* A, const void* B, int M, int N, int K, int lda, int ldb, in
   B2C_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape %d %d %d", M, N, K);
   B2C_REQUIRE(epi && epi->out0, "gemm: epilogue output missing");
   GemmParams p;
+  memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K; p.splits = 1; p.k_per_split = 0; p.epi = *epi;
   switch (mode) {
     case B2C_EPI_BF16: return dispatch_mode<B2C_EPI_BF16>(A, B, lda, ldb, a_mn, b_mn, p, stream);
@@ -484,14 +560,129 @@ int gemm(const void* A, const void* B, int M, int N, int K, int lda, int ldb, in
     case B2C_EPI_DSILU: return dispatch_mode<B2C_EPI_DSILU>(A, B, lda, ldb, a_mn, b_mn, p, stream);
     case B2C_EPI_RELU_MASK: return dispatch_mode<B2C_EPI_RELU_MASK>(A, B, lda, ldb, a_mn, b_mn, p, stream);
     case B2C_EPI_ACCUM_F32: return dispatch_mode<B2C_EPI_ACCUM_F32>(A, B, lda, ldb, a_mn, b_mn, p, stream);
+    case B2C_EPI_RELU_BWD: return dispatch_mode<B2C_EPI_RELU_BWD>(A, B, lda, ldb, a_mn, b_mn, p, stream);
   }
   set_last_error("gemm: unknown epilogue %d", mode);
   return B2C_ERR_INVALID;
 }
 
+// ---------------------------------------------------------------- 3x3 stride-2 convolution as implicit GEMM
+static int conv_map4d(CUtensorMap* m, const void* base, int C, int F, int T, int B, int box_c, int box_f, int box_t,
+                      int stride_ft) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)F, (uint64_t)T, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)C * 2, (uint64_t)F * C * 2, (uint64_t)T * F * C * 2};
+  uint32_t box[4] = {(uint32_t)box_c, (uint32_t)(box_f * stride_ft), (uint32_t)(box_t * stride_ft), 1};
+  uint32_t es[4] = {1, (uint32_t)stride_ft, (uint32_t)stride_ft, 1};
+  return make_tmap(m, base, 2, 4, dims, strides, box, es, 1);
+}
+
+int conv3x3s2_fwd(const void* in, const void* w_bf16, const float* bias, const int32_t* len_out, void* out, int B,
+                  int T1, int F1, int C, cudaStream_t stream) {
+  const int T2 = (T1 - 1) / 2 + 1, F2 = (F1 - 1) / 2 + 1;
+  B2C_REQUIRE(C % 64 == 0 && F2 >= 1 && F2 <= 128 && B > 0, "conv3x3s2_fwd: unsupported shape C=%d F2=%d", C, F2);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  ConvGeom& g = p.cv;
+  g.C = C; g.Fq = F2; g.TR = 128 / F2; g.Tq = T2; g.tiles_per_batch = (T2 + g.TR - 1) / g.TR; g.a_t_mul = 2; g.ntaps = 9;
+  for (int t = 0; t < 9; ++t) { g.tap_t[t] = t / 3 - 1; g.tap_f[t] = t % 3 - 1; g.tap_k[t] = t * C; }
+  g.To = T2; g.Fo = F2; g.ts = 1; g.fs = 1; g.pt = 0; g.pf = 0;
+  p.M = B * g.tiles_per_batch; p.N = C; p.K = 9 * (C / BK); p.splits = 1; p.k_per_split = p.K;
+  p.epi.out0 = out; p.epi.bias = bias; p.epi.lengths = len_out; p.epi.ldo = C; p.epi.rows_per_batch = T2 * F2;
+  p.epi.rows_inner = F2; p.epi.alpha = 1.f;
+  const bool wide = (C % 256 == 0);
+  CUtensorMap ta, tb;
+  int rc = conv_map4d(&ta, in, C, F1, T1, B, 64, F2, g.TR, 2);
+  if (rc) return rc;
+  uint64_t dims[2] = {(uint64_t)9 * C, (uint64_t)C}, strides[1] = {(uint64_t)9 * C * 2};
+  uint32_t box[2] = {(uint32_t)BK, (uint32_t)(wide ? 256 : 128)}, es[2] = {1, 1};
+  rc = make_tmap(&tb, w_bf16, 2, 2, dims, strides, box, es, 1);
+  if (rc) return rc;
+  if (wide) return launch_tc<256, 0, 0, B2C_EPI_RELU_MASK, 1>(ta, tb, p, stream);
+  return launch_tc<128, 0, 0, B2C_EPI_RELU_MASK, 1>(ta, tb, p, stream);
+}
+
+// dx[b,t1,f1,ci] = relu'(x[b,t1,f1,ci]) * sum_{taps,co} dy[b,(t1+1-kh)/2,(f1+1-kw)/2,co] * W[co,ci,kh,kw]
+// decomposed into the four (t1,f1) parity classes (1, 2, 2 and 4 taps): each a dense shifted-window implicit GEMM.
+int conv3x3s2_bwd_data(const void* dy, const void* wd_bf16, const void* x, void* dx, int B, int T1, int F1, int C,
+                       cudaStream_t stream) {
+  const int T2 = (T1 - 1) / 2 + 1, F2 = (F1 - 1) / 2 + 1;
+  B2C_REQUIRE(C % 64 == 0 && F2 <= 128 && B > 0, "conv3x3s2_bwd_data: unsupported shape");
+  const bool wide = (C % 256 == 0);
+  CUtensorMap tb;
+  {
+    uint64_t dims[2] = {(uint64_t)9 * C, (uint64_t)C}, strides[1] = {(uint64_t)9 * C * 2};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)(wide ? 256 : 128)}, es[2] = {1, 1};
+    int rc = make_tmap(&tb, wd_bf16, 2, 2, dims, strides, box, es, 1);
+    if (rc) return rc;
+  }
+  for (int pt = 0; pt < 2; ++pt) {
+    for (int pf = 0; pf < 2; ++pf) {
+      const int Tc = (T1 - pt + 1) / 2, Fc = (F1 - pf + 1) / 2;
+      if (Tc <= 0 || Fc <= 0) continue;
+      GemmParams p;
+      memset(&p, 0, sizeof(p));
+      ConvGeom& g = p.cv;
+      g.C = C; g.Fq = Fc; g.TR = 128 / Fc; g.Tq = Tc; g.tiles_per_batch = (Tc + g.TR - 1) / g.TR; g.a_t_mul = 1;
+      g.ntaps = 0;
+      for (int kh = 0; kh < 3; ++kh) {
+        if (((pt + 1 - kh) & 1) != 0) continue;
+        for (int kw = 0; kw < 3; ++kw) {
+          if (((pf + 1 - kw) & 1) != 0) continue;
+          g.tap_t[g.ntaps] = (pt + 1 - kh) / 2;
+          g.tap_f[g.ntaps] = (pf + 1 - kw) / 2;
+          g.tap_k[g.ntaps] = (kh * 3 + kw) * C;
+          ++g.ntaps;
+        }
+      }
+      g.To = T1; g.Fo = F1; g.ts = 2; g.fs = 2; g.pt = pt; g.pf = pf;
+      p.M = B * g.tiles_per_batch; p.N = C; p.K = g.ntaps * (C / BK); p.splits = 1; p.k_per_split = p.K;
+      p.epi.out0 = dx; p.epi.aux = x; p.epi.ldo = C; p.epi.alpha = 1.f;
+      CUtensorMap ta;
+      int rc = conv_map4d(&ta, dy, C, F2, T2, B, 64, Fc, g.TR, 1);
+      if (rc) return rc;
+      rc = wide ? launch_tc<256, 0, 0, B2C_EPI_RELU_BWD, 2>(ta, tb, p, stream)
+                : launch_tc<128, 0, 0, B2C_EPI_RELU_BWD, 2>(ta, tb, p, stream);
+      if (rc) return rc;
+    }
+  }
+  return B2C_OK;
+}
+
+// dw[co, tap*C + ci] += sum_{b,t2,f2} dy[b,t2,f2,co] * x[b,2t2+kh-1,2f2+kw-1,ci]
+int conv3x3s2_bwd_weight(const void* dy, const void* x, float* dw, int B, int T1, int F1, int C, cudaStream_t stream) {
+  const int T2 = (T1 - 1) / 2 + 1, F2 = (F1 - 1) / 2 + 1;
+  B2C_REQUIRE(C % 128 == 0 && F2 <= 64 && B > 0, "conv3x3s2_bwd_weight: unsupported shape");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  ConvGeom& g = p.cv;
+  g.C = C; g.Fq = F2; g.TR = 64 / F2; g.Tq = T2; g.tiles_per_batch = (T2 + g.TR - 1) / g.TR;
+  p.M = C; p.N = C; p.K = B * g.tiles_per_batch; p.splits = 9; p.k_per_split = p.K;
+  p.epi.out0 = dw; p.epi.ldo = 9 * C; p.epi.alpha = 1.f;
+  CUtensorMap ta, tb;
+  int rc = conv_map4d(&ta, dy, C, F2, T2, B, 64, F2, g.TR, 1);
+  if (rc) return rc;
+  rc = conv_map4d(&tb, x, C, F1, T1, B, 64, F2, g.TR, 2);
+  if (rc) return rc;
+  return launch_tc<128, 1, 1, B2C_EPI_ACCUM_F32, 3>(ta, tb, p, stream);
+}
+
 }  // namespace b2c
+
 
 extern "C" int b2c_gemm(const void* A, const void* B, int M, int N, int K, int lda, int ldb, int a_mn_major,
                         int b_mn_major, int epilogue_mode, const b2c_epilogue* epi, void* stream) {
   return b2c::gemm(A, B, M, N, K, lda, ldb, a_mn_major, b_mn_major, epilogue_mode, epi, (cudaStream_t)stream);
+}
+
+extern "C" int b2c_conv3x3s2_fwd(const void* in_bf16, const void* w_bf16, const float* bias, const int32_t* len_out,
+                                 void* out_bf16, int B, int T1, int F1, int C, void* stream) {
+  return b2c::conv3x3s2_fwd(in_bf16, w_bf16, bias, len_out, out_bf16, B, T1, F1, C, (cudaStream_t)stream);
+}
+extern "C" int b2c_conv3x3s2_bwd_data(const void* dy_bf16, const void* wd_bf16, const void* x_bf16, void* dx_bf16, int B,
+                                      int T1, int F1, int C, void* stream) {
+  return b2c::conv3x3s2_bwd_data(dy_bf16, wd_bf16, x_bf16, dx_bf16, B, T1, F1, C, (cudaStream_t)stream);
+}
+extern "C" int b2c_conv3x3s2_bwd_weight(const void* dy_bf16, const void* x_bf16, float* dw, int B, int T1, int F1, int C,
+                                        void* stream) {
+  return b2c::conv3x3s2_bwd_weight(dy_bf16, x_bf16, dw, B, T1, F1, C, (cudaStream_t)stream);
 }

@@ -1,0 +1,184 @@
+// K2: first subsampling convolution Conv2d(1→C, 3x3, stride 2, pad 1) + bias + ReLU + time masks, forward and
+// weight-gradient, on CUDA cores (C_in = 1: a 9-tap stencil, HBM-bound on its [B,T1,F1,C] bf16 output — no GEMM).
+// Reference: ConvSubsampling 'striding' / 'dw_striding' layer 0 + MaskedConvSequential
+// (nemo/collections/asr/parts/submodules/subsampling.py:142-253,725-753) under bf16 autocast
+// (inputs and weights rounded to bf16, fp32 accumulate, bf16 output).
+// Also the depthwise 3x3 stride-2 stages of dw_striding (channels-last, TMA-free register stencil).
+#include "common.cuh"
+
+namespace b2c {
+
+// one CTA per (b, t1): thread = channel pair, loop over f1.  mel [B, F, T] fp32 → out [B, T1, F1, C] bf16
+__global__ void __launch_bounds__(256)
+subsample_conv1_fwd_kernel(const float* __restrict__ mel, const float* __restrict__ w, const float* __restrict__ bias,
+                           const int32_t* __restrict__ len_in, const int32_t* __restrict__ len_out,
+                           bf16* __restrict__ out, int F, int T, int C, int T1, int F1) {
+  extern __shared__ float sx[];  // [3][F + 2]
+  const int t1 = blockIdx.x, b = blockIdx.y;
+  const int lin = len_in[b], lout = len_out[b];
+  const int FP = F + 2;
+  for (int i = threadIdx.x; i < 3 * FP; i += blockDim.x) {
+    const int kh = i / FP, fp = i - kh * FP;
+    const int t = 2 * t1 - 1 + kh, f = fp - 1;
+    float v = 0.f;
+    if (t >= 0 && t < T && t < lin && f >= 0 && f < F) v = bf16_round(mel[((size_t)b * F + f) * T + t]);
+    sx[i] = v;
+  }
+  __syncthreads();
+  const bool valid = t1 < lout;
+  for (int cp = threadIdx.x; cp * 2 < C; cp += blockDim.x) {
+    const int c = cp * 2;
+    float w0[9], w1[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      w0[j] = bf16_round(w[(size_t)c * 9 + j]);
+      w1[j] = bf16_round(w[(size_t)(c + 1) * 9 + j]);
+    }
+    const float b0 = bias[c], b1 = bias[c + 1];
+    bf16* orow = out + (((size_t)b * T1 + t1) * F1) * C + c;
+    for (int f1 = 0; f1 < F1; ++f1) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float x = sx[kh * FP + 2 * f1 + kw];
+          a0 = fmaf(w0[kh * 3 + kw], x, a0);
+          a1 = fmaf(w1[kh * 3 + kw], x, a1);
+        }
+      // conv output (bf16) → mask → ReLU → mask  (subsampling.py:731-752)
+      const float r0 = valid ? fmaxf(bf16_round(a0 + b0), 0.f) : 0.f;
+      const float r1 = valid ? fmaxf(bf16_round(a1 + b1), 0.f) : 0.f;
+      *reinterpret_cast<uint32_t*>(orow + (size_t)f1 * C) = pack_bf16(r0, r1);
+    }
+  }
+}
+
+// dW[c, kh, kw] += sum dY[b,t1,f1,c] * x[b, 2t1+kh-1, 2f1+kw-1];  db[c] += sum dY   (dY already ReLU/mask gated)
+__global__ void __launch_bounds__(256)
+subsample_conv1_bwd_kernel(const float* __restrict__ mel, const bf16* __restrict__ dy, const int32_t* __restrict__ len_in,
+                           float* __restrict__ dw, float* __restrict__ dbias, int F, int T, int C, int T1, int F1,
+                           int rows_per_cta) {
+  extern __shared__ float sx[];  // [3][F + 2]
+  const int b = blockIdx.y;
+  const int lin = len_in[b];
+  const int FP = F + 2;
+  const int t1_0 = blockIdx.x * rows_per_cta, t1_1 = min(T1, t1_0 + rows_per_cta);
+  // this implementation keeps one channel pair per thread: C <= 2 * blockDim.x * passes
+  for (int cp0 = 0; cp0 * 2 < C; cp0 += blockDim.x) {
+    const int cp = cp0 + threadIdx.x;
+    const bool act = cp * 2 < C;
+    const int c = cp * 2;
+    float g0[9], g1[9], d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) g0[j] = g1[j] = 0.f;
+    for (int t1 = t1_0; t1 < t1_1; ++t1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < 3 * FP; i += blockDim.x) {
+        const int kh = i / FP, fp = i - kh * FP;
+        const int t = 2 * t1 - 1 + kh, f = fp - 1;
+        float v = 0.f;
+        if (t >= 0 && t < T && t < lin && f >= 0 && f < F) v = bf16_round(mel[((size_t)b * F + f) * T + t]);
+        sx[i] = v;
+      }
+      __syncthreads();
+      if (act) {
+        const bf16* drow = dy + (((size_t)b * T1 + t1) * F1) * C + c;
+        for (int f1 = 0; f1 < F1; ++f1) {
+          const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(drow + (size_t)f1 * C));
+          d0 += g.x; d1 += g.y;
+#pragma unroll
+          for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const float x = sx[kh * FP + 2 * f1 + kw];
+              g0[kh * 3 + kw] = fmaf(g.x, x, g0[kh * 3 + kw]);
+              g1[kh * 3 + kw] = fmaf(g.y, x, g1[kh * 3 + kw]);
+            }
+        }
+      }
+    }
+    if (act) {
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        atomicAdd(dw + (size_t)c * 9 + j, g0[j]);
+        atomicAdd(dw + (size_t)(c + 1) * 9 + j, g1[j]);
+      }
+      atomicAdd(dbias + c, d0);
+      atomicAdd(dbias + c + 1, d1);
+    }
+  }
+}
+
+// depthwise Conv2d(C, 3x3, s2, p1, groups=C) on channels-last [B,T1,F1,C] → [B,T2,F2,C], + bias, output masked t2<len
+// (input is already time-masked by its producer).  thread = channel pair; CTA = (b, t2) row.
+__global__ void __launch_bounds__(256)
+dwconv3x3s2_fwd_kernel(const bf16* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                       const int32_t* __restrict__ len_out, bf16* __restrict__ out, int T1, int F1, int C, int T2, int F2) {
+  const int t2 = blockIdx.x, b = blockIdx.y;
+  const bool valid = len_out ? (t2 < len_out[b]) : true;
+  for (int cp = threadIdx.x; cp * 2 < C; cp += blockDim.x) {
+    const int c = cp * 2;
+    float w0[9], w1[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      w0[j] = bf16_round(w[(size_t)c * 9 + j]);
+      w1[j] = bf16_round(w[(size_t)(c + 1) * 9 + j]);
+    }
+    const float b0 = bias[c], b1 = bias[c + 1];
+    for (int f2 = 0; f2 < F2; ++f2) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int t = 2 * t2 - 1 + kh;
+        if (t < 0 || t >= T1) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int f = 2 * f2 - 1 + kw;
+          if (f < 0 || f >= F1) continue;
+          const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(in + (((size_t)b * T1 + t) * F1 + f) * C + c));
+          a0 = fmaf(w0[kh * 3 + kw], x.x, a0);
+          a1 = fmaf(w1[kh * 3 + kw], x.y, a1);
+        }
+      }
+      const uint32_t o = valid ? pack_bf16(a0 + b0, a1 + b1) : 0u;
+      *reinterpret_cast<uint32_t*>(out + (((size_t)b * T2 + t2) * F2 + f2) * C + c) = o;
+    }
+  }
+}
+
+}  // namespace b2c
+
+using namespace b2c;
+
+extern "C" int b2c_subsample_conv1_fwd(const float* mel, const float* w, const float* bias, const int32_t* len_in,
+                                       const int32_t* len_out, void* out_bf16, int B, int F, int T, int C,
+                                       void* stream) {
+  B2C_REQUIRE(C % 2 == 0 && B > 0 && T > 0 && F > 0, "subsample_conv1_fwd: bad shape");
+  const int T1 = (T + 2 - 3) / 2 + 1, F1 = (F + 2 - 3) / 2 + 1;
+  subsample_conv1_fwd_kernel<<<dim3(T1, B), 256, 3 * (F + 2) * sizeof(float), (cudaStream_t)stream>>>(
+      mel, w, bias, len_in, len_out, reinterpret_cast<bf16*>(out_bf16), F, T, C, T1, F1);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_subsample_conv1_bwd(const float* mel, const void* dout_bf16, const int32_t* len_in, float* dw,
+                                       float* dbias, int B, int F, int T, int C, void* stream) {
+  B2C_REQUIRE(C % 2 == 0 && B > 0 && T > 0 && F > 0, "subsample_conv1_bwd: bad shape");
+  const int T1 = (T + 2 - 3) / 2 + 1, F1 = (F + 2 - 3) / 2 + 1;
+  const int rows = 16;
+  subsample_conv1_bwd_kernel<<<dim3((T1 + rows - 1) / rows, B), 256, 3 * (F + 2) * sizeof(float), (cudaStream_t)stream>>>(
+      mel, reinterpret_cast<const bf16*>(dout_bf16), len_in, dw, dbias, F, T, C, T1, F1, rows);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_dwconv3x3s2_fwd(const void* in_bf16, const float* w, const float* bias, const int32_t* len_out,
+                                   void* out_bf16, int B, int T1, int F1, int C, void* stream) {
+  B2C_REQUIRE(C % 2 == 0 && B > 0 && T1 > 0 && F1 > 0, "dwconv3x3s2_fwd: bad shape");
+  const int T2 = (T1 + 2 - 3) / 2 + 1, F2 = (F1 + 2 - 3) / 2 + 1;
+  dwconv3x3s2_fwd_kernel<<<dim3(T2, B), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(in_bf16), w, bias, len_out, reinterpret_cast<bf16*>(out_bf16), T1, F1, C, T2, F2);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}

@@ -1,0 +1,596 @@
+"""B200ConformerEncoder — drop-in for `nemo.collections.asr.modules.ConformerEncoder`
+(nemo/collections/asr/modules/conformer_encoder.py:62-1220) on the full-context offline path.
+
+Same constructor kwargs, `forward(audio_signal=[B,feat_in,T], length=[B]) -> (outputs [B,d_model,T'], lengths [B] i64)`,
+attributes and state_dict key layout, so reference checkpoints load unchanged and
+`model.encoder = B200ConformerEncoder.from_reference(model.encoder)` is the integration route.
+
+The nn submodules below are parameter CONTAINERS only (their torch forward is never called): every operation of the
+forward and backward pass is a hand-written sm_100a kernel reached through the C ABI (include/b200conformer.h).
+Precision protocol = the reference under `torch.autocast(bfloat16)`: fp32 master parameters, bf16 GEMM operands with
+fp32 accumulation, fp32 LayerNorm / softmax / residual stream.  There is no CPU or eager-PyTorch fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from . import _lib as L
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+# dropout sites inside one layer (site id = layer * 16 + k); layer index n_layers is the pre-encoder dropout
+S_FF1_HID, S_FF1_OUT, S_ATT_P, S_ATT_OUT, S_CONV_OUT, S_FF2_HID, S_FF2_OUT = range(7)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# parameter containers (names / shapes = reference)
+# ----------------------------------------------------------------------------------------------------------------
+class _FeedForward(nn.Module):  # ConformerFeedForward, conformer_modules.py:366-380
+    def __init__(self, d_model, d_ff, use_bias=True):
+        super().__init__()
+        self.linear1 = nn.Linear(d_model, d_ff, bias=use_bias)
+        self.linear2 = nn.Linear(d_ff, d_model, bias=use_bias)
+
+
+class _RelPosMHA(nn.Module):  # RelPositionMultiHeadAttention, multi_head_attention.py:225-257
+    def __init__(self, n_head, n_feat):
+        super().__init__()
+        self.h, self.d_k = n_head, n_feat // n_head
+        self.linear_q = nn.Linear(n_feat, n_feat)
+        self.linear_k = nn.Linear(n_feat, n_feat)
+        self.linear_v = nn.Linear(n_feat, n_feat)
+        self.linear_out = nn.Linear(n_feat, n_feat)
+        self.linear_pos = nn.Linear(n_feat, n_feat, bias=False)
+        self.pos_bias_u = nn.Parameter(torch.zeros(n_head, self.d_k))
+        self.pos_bias_v = nn.Parameter(torch.zeros(n_head, self.d_k))
+
+
+class _ConvModule(nn.Module):  # ConformerConvolution, conformer_modules.py:254-318
+    def __init__(self, d_model, kernel_size):
+        super().__init__()
+        self.pointwise_conv1 = nn.Conv1d(d_model, 2 * d_model, 1)
+        self.depthwise_conv = nn.Conv1d(d_model, d_model, kernel_size, groups=d_model, padding=0)
+        self.batch_norm = nn.BatchNorm1d(d_model)
+        self.pointwise_conv2 = nn.Conv1d(d_model, d_model, 1)
+
+
+class _ConformerLayer(nn.Module):  # ConformerLayer, conformer_modules.py:35-158
+    def __init__(self, d_model, d_ff, n_heads, conv_kernel_size):
+        super().__init__()
+        self.norm_feed_forward1 = nn.LayerNorm(d_model)
+        self.feed_forward1 = _FeedForward(d_model, d_ff)
+        self.norm_conv = nn.LayerNorm(d_model)
+        self.conv = _ConvModule(d_model, conv_kernel_size)
+        self.norm_self_att = nn.LayerNorm(d_model)
+        self.self_attn = _RelPosMHA(n_heads, d_model)
+        self.norm_feed_forward2 = nn.LayerNorm(d_model)
+        self.feed_forward2 = _FeedForward(d_model, d_ff)
+        self.norm_out = nn.LayerNorm(d_model)
+
+
+class _ConvSubsampling(nn.Module):  # ConvSubsampling, subsampling.py:62-383 ('striding' / 'dw_striding')
+    def __init__(self, subsampling, subsampling_factor, feat_in, feat_out, conv_channels):
+        super().__init__()
+        self._subsampling, self.subsampling_factor = subsampling, subsampling_factor
+        self._conv_channels, self._feat_in, self._feat_out = conv_channels, feat_in, feat_out
+        self._sampling_num = int(math.log2(subsampling_factor))
+        layers: List[nn.Module] = []
+        cin = 1
+        if subsampling == "striding":
+            for _ in range(self._sampling_num):
+                layers += [nn.Conv2d(cin, conv_channels, 3, stride=2, padding=1), nn.ReLU(True)]
+                cin = conv_channels
+        else:  # dw_striding
+            layers += [nn.Conv2d(1, conv_channels, 3, stride=2, padding=1), nn.ReLU(True)]
+            for _ in range(self._sampling_num - 1):
+                layers += [nn.Conv2d(conv_channels, conv_channels, 3, stride=2, padding=1, groups=conv_channels),
+                           nn.Conv2d(conv_channels, conv_channels, 1), nn.ReLU(True)]
+        self.conv = nn.Sequential(*layers)
+        f = feat_in
+        for _ in range(self._sampling_num):
+            f = (f + 2 - 3) // 2 + 1
+        self._f_out = f
+        self.out = nn.Linear(conv_channels * f, feat_out)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# kernel-call helpers
+# ----------------------------------------------------------------------------------------------------------------
+def _empty(*shape, dtype=BF16, dev=None):
+    return torch.empty(*shape, dtype=dtype, device=dev)
+
+
+class _WeightCache:
+    """bf16 operand copies of the fp32 master weights in the kernels' layouts, refreshed when a parameter changes
+    (`Tensor._version` bumps on every in-place optimizer update)."""
+
+    def __init__(self):
+        self.store = {}
+
+    def get(self, key, params, build):
+        ver = tuple((p.data_ptr(), p._version) for p in params)
+        hit = self.store.get(key)
+        if hit is None or hit[0] != ver:
+            self.store[key] = (ver, build())
+            hit = self.store[key]
+        return hit[1]
+
+
+def _cast(w: torch.Tensor) -> torch.Tensor:
+    out = _empty(*w.shape, dev=w.device)
+    L.call("cast_bf16", w.detach().contiguous(), out, w.numel(), 1.0)
+    return out
+
+
+def _permute_bf16(w: torch.Tensor, A, B, C, mode) -> torch.Tensor:
+    shape = (B, A, C) if mode == 0 else (A, C, B)
+    out = _empty(*shape, dev=w.device)
+    L.call("permute3_bf16", w.detach().contiguous(), out, A, B, C, mode)
+    return out
+
+
+def _permute_f32(w: torch.Tensor, A, B, C, mode, out=None, accumulate=0) -> torch.Tensor:
+    shape = (B, A, C) if mode == 0 else (A, C, B)
+    if out is None:
+        out = _empty(*shape, dtype=F32, dev=w.device)
+    L.call("permute3_f32", w.detach().contiguous(), out, A, B, C, mode, accumulate)
+    return out
+
+
+class B200ConformerEncoder(nn.Module):
+    def __init__(
+        self, feat_in, n_layers, d_model, feat_out=-1, causal_downsampling=False, subsampling="striding",
+        subsampling_factor=4, subsampling_conv_chunking_factor=1, subsampling_conv_channels=-1, reduction=None,
+        reduction_position=None, reduction_factor=1, ff_expansion_factor=4, self_attention_model="rel_pos", n_heads=4,
+        att_context_size=None, att_context_probs=None, att_context_style="regular", xscaling=True, untie_biases=True,
+        pos_emb_max_len=5000, conv_kernel_size=31, conv_norm_type="batch_norm", conv_context_size=None, use_bias=True,
+        dropout=0.1, dropout_pre_encoder=0.1, dropout_emb=0.1, dropout_att=0.0, stochastic_depth_drop_prob: float = 0.0,
+        stochastic_depth_mode: str = "linear", stochastic_depth_start_layer: int = 1, global_tokens: int = 0,
+        global_tokens_spacing: int = 1, global_attn_separate: bool = False, use_pytorch_sdpa: bool = False,
+        use_pytorch_sdpa_backends=None, sync_max_audio_length: bool = True,
+    ):
+        super().__init__()
+        bad = []
+        if causal_downsampling: bad.append("causal_downsampling")
+        if subsampling not in ("striding", "dw_striding"): bad.append(f"subsampling={subsampling}")
+        if subsampling == "striding" and subsampling_factor != 4: bad.append("striding needs subsampling_factor=4")
+        if subsampling == "dw_striding" and subsampling_factor != 8: bad.append("dw_striding needs subsampling_factor=8")
+        if reduction: bad.append("reduction")
+        if self_attention_model != "rel_pos": bad.append(f"self_attention_model={self_attention_model}")
+        if att_context_size not in (None, [-1, -1], (-1, -1)): bad.append("att_context_size")
+        if att_context_style != "regular": bad.append("att_context_style")
+        if not untie_biases: bad.append("untie_biases=False")
+        if conv_norm_type != "batch_norm": bad.append(f"conv_norm_type={conv_norm_type}")
+        if conv_context_size is not None: bad.append("conv_context_size")
+        if not use_bias: bad.append("use_bias=False")
+        if stochastic_depth_drop_prob != 0.0: bad.append("stochastic_depth")
+        if global_tokens: bad.append("global_tokens")
+        if feat_out > 0 and feat_out != d_model: bad.append("feat_out projection")
+        if d_model % n_heads or (d_model // n_heads) not in (64, 128): bad.append("head dim must be 64 or 128")
+        if conv_kernel_size not in (31, 9, 5): bad.append(f"conv_kernel_size={conv_kernel_size}")
+        if dropout_emb not in (0, 0.0): bad.append("dropout_emb>0 (YAML recipes use 0.0)")
+        if d_model % 64: bad.append("d_model % 64")
+        if bad:
+            raise NotImplementedError("B200ConformerEncoder (hot-path subset, SURVEY.md §8): unsupported " + ", ".join(bad))
+        self.d_model, self.n_layers, self._feat_in, self._feat_out = d_model, n_layers, feat_in, d_model
+        self.n_heads, self.d_ff = n_heads, d_model * ff_expansion_factor
+        self.conv_kernel_size = conv_kernel_size
+        self.subsampling, self.subsampling_factor = subsampling, subsampling_factor
+        self.subsampling_conv_chunking_factor = subsampling_conv_chunking_factor
+        self.self_attention_model, self.att_context_style = self_attention_model, att_context_style
+        self.att_context_size = [-1, -1]
+        self.xscale = math.sqrt(d_model) if xscaling else None
+        self.dropout, self.dropout_pre_encoder, self.dropout_att = dropout, dropout_pre_encoder, dropout_att
+        self.pos_emb_max_len, self.max_audio_length = pos_emb_max_len, pos_emb_max_len
+        # the reference all-reduces max length every forward (conformer_encoder.py:770-776): removed, the relative
+        # position table is generated on the fly for the actual T (no host sync, no collective)
+        self.sync_max_audio_length = False
+        self.use_pad_mask, self.export_cache_support, self.streaming_cfg = True, False, None
+        self.layer_drop_probs = [0.0] * n_layers
+        conv_channels = d_model if subsampling_conv_channels == -1 else subsampling_conv_channels
+        self.pre_encode = _ConvSubsampling(subsampling, subsampling_factor, feat_in, d_model, conv_channels)
+        self.layers = nn.ModuleList(_ConformerLayer(d_model, self.d_ff, n_heads, conv_kernel_size) for _ in range(n_layers))
+        self.out_proj = None
+        self._wc = _WeightCache()
+        self._step = 0
+        self._pos_cache = {}
+
+    # ---- reference API surface that callers touch (ctc_models.py / mixins) ------------------------------------
+    def set_max_audio_length(self, max_audio_length):
+        self.max_audio_length = max_audio_length
+
+    def freeze(self):
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self.eval()
+
+    def unfreeze(self):
+        for p in self.parameters():
+            p.requires_grad_(True)
+        self.train()
+
+    def _unsupported(self, *a, **k):
+        raise NotImplementedError("streaming / export / attention-model switching are outside the accelerated hot path")
+
+    setup_streaming_params = get_initial_cache_state = cache_aware_stream_step = change_attention_model = _unsupported
+    change_subsampling_conv_chunking_factor = _unsupported
+
+    @classmethod
+    def from_reference(cls, ref, **overrides):
+        """Build from a live reference ConformerEncoder (same weights, same hyper-parameters)."""
+        l0 = ref.layers[0]
+        pe = ref.pre_encode
+        kw = dict(
+            feat_in=ref._feat_in, n_layers=len(ref.layers), d_model=ref.d_model, subsampling=pe._subsampling,
+            subsampling_factor=pe.subsampling_factor, subsampling_conv_channels=pe._conv_channels,
+            ff_expansion_factor=l0.feed_forward1.d_ff // ref.d_model, n_heads=l0.self_attn.h,
+            conv_kernel_size=l0.conv.kernel_size, xscaling=ref.xscale is not None, dropout=l0.dropout.p,
+            dropout_pre_encoder=ref.pos_enc.dropout.p, dropout_emb=0.0, dropout_att=l0.self_attn.dropout_rate,
+        )
+        kw.update(overrides)
+        new = cls(**kw)
+        missing, unexpected = new.load_state_dict(ref.state_dict(), strict=False)
+        assert not missing, missing
+        dev = next(ref.parameters()).device
+        return new.to(dev).train(ref.training)
+
+    # ---- forward ----------------------------------------------------------------------------------------------
+    def forward(self, audio_signal, length=None, cache_last_channel=None, cache_last_time=None,
+                cache_last_channel_len=None, bypass_pre_encode=False):
+        if cache_last_channel is not None or cache_last_time is not None or bypass_pre_encode:
+            raise NotImplementedError("cache-aware streaming / bypass_pre_encode are outside the accelerated hot path")
+        if audio_signal.shape[-2] != self._feat_in:  # conformer_encoder.py:569-573
+            raise ValueError(
+                f"If bypass_pre_encode is False, audio_signal should have shape (batch, {self._feat_in}, n_frame) "
+                f"but got last dimension {audio_signal.shape[-2]}.")
+        if not audio_signal.is_cuda:
+            raise RuntimeError("B200ConformerEncoder runs on CUDA tensors only (no CPU fallback)")
+        if length is None:
+            length = audio_signal.new_full((audio_signal.size(0),), audio_signal.size(-1), dtype=torch.int64)
+        params = [p for _, p in self.named_parameters()]
+        out, out_len = _EncoderFn.apply(self, audio_signal, length, *params)
+        return out, out_len
+
+    def _seed(self):
+        self._step += 1
+        return (torch.initial_seed() * 1000003 + self._step) & 0xFFFFFFFFFFFFFFFF
+
+    # bf16 operand preparation ------------------------------------------------------------------------------------
+    def _weights(self):
+        wc, pe = self._wc, self.pre_encode
+        C, F2, d = pe._conv_channels, pe._f_out, self.d_model
+        W = {}
+        if self.subsampling == "striding":
+            w2 = pe.conv[2].weight
+            W["conv2"] = wc.get("conv2", [w2], lambda: _permute_bf16(w2, C, C, 9, 1).view(C, 9 * C))       # [co, tap, ci]
+            W["conv2_d"] = wc.get("conv2_d", [w2], lambda: _permute_bf16(_permute_f32(w2, C, C, 9, 0), C, C, 9, 1).view(C, 9 * C))  # [ci, tap, co]
+        else:
+            for i in (3, 6):
+                wpw = pe.conv[i].weight
+                W[f"pw{i}"] = wc.get(f"pw{i}", [wpw], lambda wpw=wpw: _cast(wpw).view(C, C))
+        wo = pe.out.weight
+        W["out"] = wc.get("out", [wo], lambda: _permute_bf16(wo, d, C, F2, 1).view(d, F2 * C))               # [n, f, c]
+        for i, lyr in enumerate(self.layers):
+            for nm, ff in (("ff1", lyr.feed_forward1), ("ff2", lyr.feed_forward2)):
+                W[f"{i}.{nm}.w1"] = wc.get(f"{i}.{nm}.w1", [ff.linear1.weight], lambda ff=ff: _cast(ff.linear1.weight))
+                W[f"{i}.{nm}.w2"] = wc.get(f"{i}.{nm}.w2", [ff.linear2.weight], lambda ff=ff: _cast(ff.linear2.weight))
+            at = lyr.self_attn
+            qkv = [at.linear_q.weight, at.linear_k.weight, at.linear_v.weight]
+            W[f"{i}.qkv"] = wc.get(f"{i}.qkv", qkv, lambda qkv=qkv: torch.cat([_cast(w) for w in qkv], 0))
+            qkvb = [at.linear_q.bias, at.linear_k.bias, at.linear_v.bias]
+            W[f"{i}.qkv_b"] = wc.get(f"{i}.qkv_b", qkvb, lambda qkvb=qkvb: torch.cat([b.detach() for b in qkvb], 0))
+            W[f"{i}.pos"] = wc.get(f"{i}.pos", [at.linear_pos.weight], lambda at=at: _cast(at.linear_pos.weight))
+            W[f"{i}.o"] = wc.get(f"{i}.o", [at.linear_out.weight], lambda at=at: _cast(at.linear_out.weight))
+            cv = lyr.conv
+            w1, b1 = cv.pointwise_conv1.weight, cv.pointwise_conv1.bias
+            # GLU value/gate interleave: rows (j, j+d) of [2d, d] → rows (2j, 2j+1)
+            W[f"{i}.pw1"] = wc.get(f"{i}.pw1", [w1], lambda w1=w1: _permute_bf16(w1, 2, d, d, 0).view(2 * d, d))
+            W[f"{i}.pw1_b"] = wc.get(f"{i}.pw1_b", [b1], lambda b1=b1: _permute_f32(b1, 2, d, 1, 0).view(2 * d))
+            W[f"{i}.pw2"] = wc.get(f"{i}.pw2", [cv.pointwise_conv2.weight], lambda cv=cv: _cast(cv.pointwise_conv2.weight).view(d, d))
+        return W
+
+    def _pos_table(self, T, dev):
+        key = (T, str(dev))
+        if key not in self._pos_cache:
+            p16 = _empty(2 * T - 1, self.d_model, dev=dev)
+            L.call("relpos_table", p16, None, T, self.d_model)
+            self._pos_cache = {key: p16}
+        return self._pos_cache[key]
+
+
+def _gemm(A, Bm, M, N, K, mode, *, a_mn=0, b_mn=0, lda=None, ldb=None, **kw):
+    lda = (M if a_mn else K) if lda is None else lda
+    ldb = (N if b_mn else K) if ldb is None else ldb
+    L.gemm(A, Bm, M, N, K, lda, ldb, a_mn, b_mn, mode, **kw)
+
+
+class _EncoderFn(torch.autograd.Function):
+    """Whole-encoder autograd node: forward launches the fused kernels and keeps the activations the backward
+    kernels need; backward produces all parameter gradients into ONE flat fp32 buffer (views are returned per
+    parameter — the data-parallel all-reduce runs over that single buffer)."""
+
+    @staticmethod
+    def forward(ctx, enc: B200ConformerEncoder, mel, length, *params):
+        dev = mel.device
+        training = enc.training
+        B, Fm, Tm = mel.shape
+        d, H, dff, k = enc.d_model, enc.n_heads, enc.d_ff, enc.conv_kernel_size
+        dk = d // H
+        pe = enc.pre_encode
+        C, F2, n_conv = pe._conv_channels, pe._f_out, pe._sampling_num
+        mel = mel.detach().to(F32).contiguous()
+        length = length.detach().to(device=dev, dtype=torch.int64).contiguous()
+        seed = enc._seed() if training else 0
+        p_drop = enc.dropout if training else 0.0
+        p_pre = enc.dropout_pre_encoder if training else 0.0
+        p_att = enc.dropout_att if training else 0.0
+        W = enc._weights()
+        S = {}  # saved activations
+
+        # ---- lengths (subsampling.py:576-586) ---------------------------------------------------------------
+        len_in32 = _empty(B, dtype=torch.int32, dev=dev)
+        len_stage = _empty(n_conv * B, dtype=torch.int32, dev=dev)
+        out_len = _empty(B, dtype=torch.int64, dev=dev)
+        L.call("subsample_lengths", length, len_in32, len_stage, out_len, B, n_conv)
+        lens = [len_stage[i * B:(i + 1) * B] for i in range(n_conv)]
+        Ts, Fs = [Tm], [Fm]
+        for _ in range(n_conv):
+            Ts.append((Ts[-1] - 1) // 2 + 1)
+            Fs.append((Fs[-1] - 1) // 2 + 1)
+        T = Ts[-1]
+        M = B * T
+        enc_len32 = lens[-1]
+
+        # ---- subsampling -------------------------------------------------------------------------------------
+        x1 = _empty(B, Ts[1], Fs[1], C, dev=dev)
+        L.call("subsample_conv1_fwd", mel, pe.conv[0].weight.detach(), pe.conv[0].bias.detach(), len_in32, lens[0], x1,
+               B, Fm, Tm, C)
+        if enc.subsampling == "striding":
+            x2 = _empty(B, Ts[2], Fs[2], C, dev=dev)
+            L.call("conv3x3s2_fwd", x1, W["conv2"], pe.conv[2].bias.detach(), lens[1], x2, B, Ts[1], Fs[1], C)
+            S["sub"] = (x1, x2)
+            xlast = x2
+        else:
+            acts = [x1]
+            cur = x1
+            for s_i, ci in enumerate((2, 5)):
+                dwo = _empty(B, Ts[s_i + 2], Fs[s_i + 2], C, dev=dev)
+                L.call("dwconv3x3s2_fwd", cur, pe.conv[ci].weight.detach(), pe.conv[ci].bias.detach(), lens[s_i + 1],
+                       dwo, B, Ts[s_i + 1], Fs[s_i + 1], C)
+                rows = B * Ts[s_i + 2] * Fs[s_i + 2]
+                pwo = _empty(B, Ts[s_i + 2], Fs[s_i + 2], C, dev=dev)
+                _gemm(dwo, W[f"pw{ci + 1}"], rows, C, C, L.EPI_RELU_MASK, out0=pwo, bias=pe.conv[ci + 1].bias.detach(),
+                      lengths=lens[s_i + 1], rows_per_batch=Ts[s_i + 2] * Fs[s_i + 2], rows_inner=Fs[s_i + 2])
+                acts += [dwo, pwo]
+                cur = pwo
+            S["sub"] = tuple(acts)
+            xlast = cur
+        x = _empty(M, d, dtype=F32, dev=dev)
+        _gemm(xlast, W["out"], M, d, F2 * C, L.EPI_RESID_F32, out0=x, bias=pe.out.bias.detach(),
+              alpha=enc.xscale or 1.0, seed=seed, drop_site=enc.n_layers * 16, drop_p=p_pre)
+        pos16 = enc._pos_table(T, dev)
+
+        # ---- conformer layers ---------------------------------------------------------------------------------
+        layers_saved = []
+        for li, lyr in enumerate(enc.layers):
+            sv = {}
+            site = li * 16
+
+            def ln(xin, norm, want32=False):
+                y16 = _empty(M, d, dev=dev)
+                y32 = _empty(M, d, dtype=F32, dev=dev) if want32 else None
+                mean, rstd = _empty(M, dtype=F32, dev=dev), _empty(M, dtype=F32, dev=dev)
+                L.call("layernorm_fwd", xin, norm.weight.detach(), norm.bias.detach(), None if want32 else y16, y32, mean,
+                       rstd, M, d)
+                return (y32 if want32 else y16), mean, rstd
+
+            def ffn(xin, norm, ff, name, s_hid, s_out):
+                y, mean, rstd = ln(xin, norm)
+                z, h = _empty(M, dff, dev=dev), _empty(M, dff, dev=dev)
+                _gemm(y, W[f"{li}.{name}.w1"], M, dff, d, L.EPI_SILU, out0=z, out1=h, bias=ff.linear1.bias.detach(),
+                      seed=seed, drop_site=site + s_hid, drop_p=p_drop)
+                xo = _empty(M, d, dtype=F32, dev=dev)
+                _gemm(h, W[f"{li}.{name}.w2"], M, d, dff, L.EPI_RESID_F32, out0=xo, aux=xin, bias=ff.linear2.bias.detach(),
+                      alpha=0.5, seed=seed, drop_site=site + s_out, drop_p=p_drop)
+                sv[name] = (xin, y, mean, rstd, z, h)
+                return xo
+
+            xa = ffn(x, lyr.norm_feed_forward1, lyr.feed_forward1, "ff1", S_FF1_HID, S_FF1_OUT)
+            # self-attention
+            at = lyr.self_attn
+            y2, m2, r2 = ln(xa, lyr.norm_self_att)
+            qkv = _empty(M, 3 * d, dev=dev)
+            _gemm(y2, W[f"{li}.qkv"], M, 3 * d, d, L.EPI_BF16, out0=qkv, bias=W[f"{li}.qkv_b"])
+            pp = _empty(2 * T - 1, d, dev=dev)
+            _gemm(pos16, W[f"{li}.pos"], 2 * T - 1, d, d, L.EPI_BF16, out0=pp)
+            ctxv = _empty(M, d, dev=dev)
+            lse = _empty(B, H, T, dtype=F32, dev=dev)
+            L.call("relpos_attn_fwd", qkv, pp, at.pos_bias_u.detach(), at.pos_bias_v.detach(), enc_len32, ctxv, lse, B, T,
+                   H, dk, p_att, seed, site + S_ATT_P)
+            xb = _empty(M, d, dtype=F32, dev=dev)
+            _gemm(ctxv, W[f"{li}.o"], M, d, d, L.EPI_RESID_F32, out0=xb, aux=xa, bias=at.linear_out.bias.detach(), alpha=1.0,
+                  seed=seed, drop_site=site + S_ATT_OUT, drop_p=p_drop)
+            sv["att"] = (xa, y2, m2, r2, qkv, pp, ctxv, lse)
+            # convolution module
+            cv = lyr.conv
+            y3, m3, r3 = ln(xb, lyr.norm_conv)
+            g = _empty(M, 2 * d, dev=dev)
+            u = _empty(M, d, dev=dev)
+            _gemm(y3, W[f"{li}.pw1"], M, 2 * d, d, L.EPI_GLU_MASK, out0=g, out1=u, bias=W[f"{li}.pw1_b"], lengths=enc_len32,
+                  rows_per_batch=T)
+            c = _empty(M, d, dev=dev)
+            bn = cv.batch_norm
+            stats = torch.zeros(2, d, dtype=F32, device=dev)
+            L.call("dwconv_fwd", u, cv.depthwise_conv.weight.detach(), cv.depthwise_conv.bias.detach(), c,
+                   stats[0] if training else None, stats[1] if training else None, B, T, d, k)
+            bnp = _empty(4, d, dtype=F32, dev=dev)  # scale, shift, mean, rstd
+            L.call("bn_finalize", stats[0], stats[1], bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+                   bnp[0], bnp[1], bnp[2], bnp[3], M, d, 1 if training else 0, bn.momentum, bn.eps)
+            if training:
+                bn.num_batches_tracked += 1
+            s_ = _empty(M, d, dev=dev)
+            L.call("bn_silu_fwd", c, bnp[0], bnp[1], s_, M, d)
+            xc = _empty(M, d, dtype=F32, dev=dev)
+            _gemm(s_, W[f"{li}.pw2"], M, d, d, L.EPI_RESID_F32, out0=xc, aux=xb, bias=cv.pointwise_conv2.bias.detach(),
+                  alpha=1.0, seed=seed, drop_site=site + S_CONV_OUT, drop_p=p_drop)
+            sv["conv"] = (xb, y3, m3, r3, g, u, c, bnp, s_)
+            xd = ffn(xc, lyr.norm_feed_forward2, lyr.feed_forward2, "ff2", S_FF2_HID, S_FF2_OUT)
+            xo, m5, r5 = ln(xd, lyr.norm_out, want32=True)
+            sv["out"] = (xd, m5, r5)
+            layers_saved.append(sv)
+            x = xo
+
+        ctx.enc, ctx.S, ctx.layers_saved, ctx.W = enc, S, layers_saved, W
+        ctx.meta = dict(B=B, T=T, M=M, Ts=Ts, Fs=Fs, seed=seed, p_drop=p_drop, p_pre=p_pre, p_att=p_att, training=training,
+                        mel=mel, len_in32=len_in32, lens=lens, pos16=pos16, xlast=xlast, nparams=len(params))
+        ctx.mark_non_differentiable(out_len)
+        ctx.set_materialize_grads(False)
+        out = x.view(B, T, d).transpose(1, 2)  # conformer_encoder.py:745
+        return out, out_len
+
+    @staticmethod
+    def backward(ctx, dout, _dlen):
+        enc: B200ConformerEncoder = ctx.enc
+        mt, W = ctx.meta, ctx.W
+        B, T, M = mt["B"], mt["T"], mt["M"]
+        seed, p_drop, p_pre, p_att, training = mt["seed"], mt["p_drop"], mt["p_pre"], mt["p_att"], mt["training"]
+        d, H, dff, k = enc.d_model, enc.n_heads, enc.d_ff, enc.conv_kernel_size
+        dk = d // H
+        dev = dout.device
+        pe = enc.pre_encode
+        C, F2 = pe._conv_channels, pe._f_out
+        names = [n for n, _ in enc.named_parameters()]
+        plist = [p for _, p in enc.named_parameters()]
+        # one flat fp32 gradient buffer; per-parameter views
+        sizes = [p.numel() for p in plist]
+        flat = torch.zeros(sum(sizes), dtype=F32, device=dev)
+        G, off = {}, 0
+        for n, p, sz in zip(names, plist, sizes):
+            G[n] = flat[off:off + sz].view_as(p)
+            off += sz
+        enc._last_flat_grad = flat
+
+        dr = dout.transpose(1, 2).contiguous().view(M, d).to(F32)
+        t16 = _empty(M, d, dev=dev)
+
+        def ln_bwd(dy, dy_bf16, xin, norm_name, norm, mean, rstd, accumulate, nxt, nscale, site, p):
+            L.call("layernorm_bwd", dy, dy_bf16, xin, norm.weight.detach(), mean, rstd, dr, accumulate,
+                   G[norm_name + ".weight"], G[norm_name + ".bias"], nxt, nscale, p, seed, site, M, d)
+
+        def wgrad(dy, N_, x_, K_, gout, alpha=1.0):
+            """gout[N_, K_] += dy[M, N_]^T @ x_[M, K_]   (contraction over tokens, both operands MN-major)"""
+            _gemm(dy, x_, N_, K_, M, L.EPI_ACCUM_F32, a_mn=1, b_mn=1, lda=N_, ldb=K_, out0=gout, ldo=K_, alpha=alpha)
+
+        for li in range(enc.n_layers - 1, -1, -1):
+            lyr, sv, pfx, site = enc.layers[li], ctx.layers_saved[li], f"layers.{li}.", li * 16
+            xd, m5, r5 = sv["out"]
+            # norm_out: dr := LN'(dr); t16 = bf16(0.5 * drop(dr)) feeds feed_forward2.linear2
+            ln_bwd(dr, 0, xd, pfx + "norm_out", lyr.norm_out, m5, r5, 0, t16, 0.5, site + S_FF2_OUT, p_drop)
+
+            def ffn_bwd(name, ff, norm_name, norm, s_hid, nxt, nscale, nsite, np_):
+                xin, y, mean, rstd, z, h = sv[name]
+                wgrad(t16, d, h, dff, G[f"{pfx}{name}.linear2.weight"])
+                L.call("colsum_bf16", t16, G[f"{pfx}{name}.linear2.bias"], M, d, d)
+                dz = _empty(M, dff, dev=dev)
+                _gemm(t16, W[f"{li}.{'ff1' if name == 'feed_forward1' else 'ff2'}.w2"], M, dff, d, L.EPI_DSILU, b_mn=1,
+                      ldb=dff, out0=dz, aux=z, seed=seed, drop_site=site + s_hid, drop_p=p_drop)
+                wgrad(dz, dff, y, d, G[f"{pfx}{name}.linear1.weight"])
+                L.call("colsum_bf16", dz, G[f"{pfx}{name}.linear1.bias"], M, dff, dff)
+                dy = _empty(M, d, dev=dev)
+                _gemm(dz, W[f"{li}.{'ff1' if name == 'feed_forward1' else 'ff2'}.w1"], M, d, dff, L.EPI_BF16, b_mn=1, ldb=d,
+                      out0=dy)
+                ln_bwd(dy, 1, xin, pfx + norm_name, norm, mean, rstd, 1, nxt, nscale, nsite, np_)
+
+            sv["feed_forward2"], sv["feed_forward1"] = sv["ff2"], sv["ff1"]
+            ffn_bwd("feed_forward2", lyr.feed_forward2, "norm_feed_forward2", lyr.norm_feed_forward2, S_FF2_HID, t16, 1.0,
+                    site + S_CONV_OUT, p_drop)
+            # ---- convolution module (t16 = bf16(drop(dr)) = gradient of pointwise_conv2's output)
+            xb, y3, m3, r3, g, u, c, bnp, s_ = sv["conv"]
+            cv = lyr.conv
+            wgrad(t16, d, s_, d, G[pfx + "conv.pointwise_conv2.weight"].view(d, d))
+            L.call("colsum_bf16", t16, G[pfx + "conv.pointwise_conv2.bias"], M, d, d)
+            ds = _empty(M, d, dev=dev)
+            _gemm(t16, W[f"{li}.pw2"], M, d, d, L.EPI_BF16, b_mn=1, ldb=d, out0=ds)
+            sums = torch.zeros(2, d, dtype=F32, device=dev)
+            L.call("bn_silu_bwd_reduce", ds, c, bnp[0], bnp[1], bnp[2], bnp[3], sums[0], sums[1], M, d)
+            dc = _empty(M, d, dev=dev)
+            L.call("bn_silu_bwd_apply", ds, c, cv.batch_norm.weight.detach(), bnp[0], bnp[1], bnp[2], bnp[3], sums[0],
+                   sums[1], dc, G[pfx + "conv.batch_norm.weight"], G[pfx + "conv.batch_norm.bias"], M, d,
+                   1 if training else 0)
+            du = _empty(M, d, dev=dev)
+            L.call("dwconv_bwd", dc, u, cv.depthwise_conv.weight.detach(), mt["lens"][-1], du,
+                   G[pfx + "conv.depthwise_conv.weight"], G[pfx + "conv.depthwise_conv.bias"], B, T, d, k)
+            dg = _empty(M, 2 * d, dev=dev)
+            L.call("glu_bwd", du, g, dg, M, d)
+            gw = torch.zeros(2 * d, d, dtype=F32, device=dev)  # interleaved layout
+            wgrad(dg, 2 * d, y3, d, gw)
+            _permute_f32(gw, d, 2, d, 0, out=G[pfx + "conv.pointwise_conv1.weight"], accumulate=1)
+            gb = torch.zeros(2 * d, dtype=F32, device=dev)
+            L.call("colsum_bf16", dg, gb, M, 2 * d, 2 * d)
+            _permute_f32(gb, d, 2, 1, 0, out=G[pfx + "conv.pointwise_conv1.bias"], accumulate=1)
+            dy3 = _empty(M, d, dev=dev)
+            _gemm(dg, W[f"{li}.pw1"], M, d, 2 * d, L.EPI_BF16, b_mn=1, ldb=d, out0=dy3)
+            ln_bwd(dy3, 1, xb, pfx + "norm_conv", lyr.norm_conv, m3, r3, 1, t16, 1.0, site + S_ATT_OUT, p_drop)
+            # ---- self-attention (t16 = gradient of linear_out's output)
+            xa, y2, m2, r2, qkv, pp, ctxv, lse = sv["att"]
+            at = lyr.self_attn
+            wgrad(t16, d, ctxv, d, G[pfx + "self_attn.linear_out.weight"])
+            L.call("colsum_bf16", t16, G[pfx + "self_attn.linear_out.bias"], M, d, d)
+            dctx = _empty(M, d, dev=dev)
+            _gemm(t16, W[f"{li}.o"], M, d, d, L.EPI_BF16, b_mn=1, ldb=d, out0=dctx)
+            dqkv = _empty(M, 3 * d, dev=dev)
+            dpos = torch.zeros(2 * T - 1, d, dtype=F32, device=dev)
+            nbytes = L.lib.b2c_relpos_attn_bwd_workspace(B, T, H)
+            ws = enc.__dict__.get("_attn_ws")
+            if ws is None or ws.numel() < nbytes or ws.device != dev:
+                ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                enc.__dict__["_attn_ws"] = ws
+            L.call("relpos_attn_bwd", qkv, pp, at.pos_bias_u.detach(), at.pos_bias_v.detach(), mt["lens"][-1], ctxv, dctx, lse,
+                   dqkv, dpos, G[pfx + "self_attn.pos_bias_u"], G[pfx + "self_attn.pos_bias_v"], ws, nbytes, B, T, H, dk,
+                   p_att, seed, site + S_ATT_P)
+            gqkv = torch.zeros(3 * d, d, dtype=F32, device=dev)
+            wgrad(dqkv, 3 * d, y2, d, gqkv)
+            gqb = torch.zeros(3 * d, dtype=F32, device=dev)
+            L.call("colsum_bf16", dqkv, gqb, M, 3 * d, 3 * d)
+            for j, nm in enumerate(("linear_q", "linear_k", "linear_v")):
+                G[f"{pfx}self_attn.{nm}.weight"].add_(gqkv[j * d:(j + 1) * d])
+                G[f"{pfx}self_attn.{nm}.bias"].add_(gqb[j * d:(j + 1) * d])
+            dpos16 = _empty(2 * T - 1, d, dev=dev)
+            L.call("cast_bf16", dpos, dpos16, dpos.numel(), 1.0)
+            _gemm(dpos16, mt["pos16"], d, d, 2 * T - 1, L.EPI_ACCUM_F32, a_mn=1, b_mn=1, lda=d, ldb=d,
+                  out0=G[pfx + "self_attn.linear_pos.weight"], ldo=d)
+            dy2 = _empty(M, d, dev=dev)
+            _gemm(dqkv, W[f"{li}.qkv"], M, d, 3 * d, L.EPI_BF16, b_mn=1, ldb=d, out0=dy2)
+            ln_bwd(dy2, 1, xa, pfx + "norm_self_att", lyr.norm_self_att, m2, r2, 1, t16, 0.5, site + S_FF1_OUT, p_drop)
+            # ---- feed_forward1
+            ffn_bwd("feed_forward1", lyr.feed_forward1, "norm_feed_forward1", lyr.norm_feed_forward1, S_FF1_HID, None, 1.0,
+                    0, 0.0)
+
+        # ---- pre_encode: xscale + dropout backward, out Linear, convolutions
+        L.call("scale_drop_cast", dr, t16, M * d, enc.xscale or 1.0, p_pre, seed, enc.n_layers * 16)
+        xlast = mt["xlast"]
+        gw = torch.zeros(d, F2 * C, dtype=F32, device=dev)
+        wgrad(t16, d, xlast.view(M, F2 * C), F2 * C, gw)
+        _permute_f32(gw, d, F2, C, 1, out=G["pre_encode.out.weight"], accumulate=1)
+        L.call("colsum_bf16", t16, G["pre_encode.out.bias"], M, d, d)
+        dylast = _empty(M, F2 * C, dev=dev)
+        _gemm(t16, W["out"], M, F2 * C, d, L.EPI_RELU_BWD, b_mn=1, ldb=F2 * C, out0=dylast, aux=xlast.view(M, F2 * C))
+        Ts, Fs, lens = mt["Ts"], mt["Fs"], mt["lens"]
+        if enc.subsampling == "striding":
+            x1, x2 = ctx.S["sub"]
+            gw2 = torch.zeros(C, 9 * C, dtype=F32, device=dev)
+            L.call("conv3x3s2_bwd_weight", dylast, x1, gw2, B, Ts[1], Fs[1], C)
+            _permute_f32(gw2, C, 9, C, 1, out=G["pre_encode.conv.2.weight"], accumulate=1)
+            L.call("colsum_bf16", dylast, G["pre_encode.conv.2.bias"], B * Ts[2] * Fs[2], C, C)
+            dx1 = _empty(B, Ts[1], Fs[1], C, dev=dev)
+            L.call("conv3x3s2_bwd_data", dylast, W["conv2_d"], x1, dx1, B, Ts[1], Fs[1], C)
+            L.call("subsample_conv1_bwd", mt["mel"], dx1, mt["len_in32"], G["pre_encode.conv.0.weight"],
+                   G["pre_encode.conv.0.bias"], B, Fs[0], Ts[0], C)
+        else:
+            raise NotImplementedError("dw_striding backward is not built yet (forward / inference only)")
+        grads = [G[n] if p.requires_grad else None for n, p in zip(names, plist)]
+        return (None, None, None, *grads)

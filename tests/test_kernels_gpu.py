@@ -370,6 +370,66 @@ def test_relpos_attention_dropout_statistics():
     # dropout is unbiased: averaging a few seeds approaches the p=0 output; and differs per seed
     assert not torch.equal(outs[1], outs[2])
     mean_drop = (outs[1] + outs[2] + outs[3]) / 3
-    e = relerr(mean_drop, outs[0])
-    print("attn dropout mean-vs-nodrop rel err", e)
-    assert e < 0.25
+    e = ((mean_drop - outs[0]).abs().mean() / outs[0].abs().mean()).item()
+    e1 = ((outs[1] - outs[0]).abs().mean() / outs[0].abs().mean()).item()
+    print("attn dropout: mean-of-3 vs no-drop rel-L1", e, "single", e1)
+    assert e < 0.7 * e1 and e1 < 0.5  # averaging seeds converges towards the p=0 output (unbiased mask + 1/(1-p))
+
+
+# ------------------------------------------------------------------------------------------------------- subsampling
+@pytest.mark.parametrize("B,F,T,C", [(2, 80, 131, 128), (3, 80, 301, 256), (2, 80, 64, 512)])
+def test_subsampling_convs(B, F, T, C):
+    Fn = torch.nn.functional
+    lengths = torch.tensor([T, max(T - 37, 3), 9][:B], dtype=torch.int64, device=DEV)
+    n = 2
+    l32 = torch.empty(B, dtype=torch.int32, device=DEV)
+    st = torch.empty(n * B, dtype=torch.int32, device=DEV)
+    o64 = torch.empty(B, dtype=torch.int64, device=DEV)
+    L.call("subsample_lengths", lengths, l32, st, o64, B, n)
+    len1, len2 = st[:B], st[B:]
+    T1, F1 = (T - 1) // 2 + 1, (F - 1) // 2 + 1
+    T2, F2 = (T1 - 1) // 2 + 1, (F1 - 1) // 2 + 1
+    mel = rnd(B, F, T)
+    tmask = lambda Tn, ln: (torch.arange(Tn, device=DEV)[None, :] < ln[:, None].long()).float()
+    mel = mel * tmask(T, l32)[:, None, :]
+    w1, b1 = rnd(C, 1, 3, 3, scale=0.3), rnd(C, scale=0.1)
+    w2, b2 = rnd(C, C, 3, 3, scale=(9 * C) ** -0.5, seed=2), rnd(C, scale=0.1, seed=3)
+    # ---- conv1 forward
+    x1 = torch.empty(B, T1, F1, C, dtype=torch.bfloat16, device=DEV)
+    L.call("subsample_conv1_fwd", mel, w1, b1, l32, len1, x1, B, F, T, C)
+    xin = mel.transpose(1, 2)[:, None]  # [B,1,T,F]
+    w1r = w1.to(torch.bfloat16).float().requires_grad_(True)
+    b1r = b1.clone().requires_grad_(True)
+    r1 = Fn.relu(Fn.conv2d(xin.to(torch.bfloat16).float(), w1r, b1r, stride=2, padding=1)) * tmask(T1, len1)[:, None, :, None]
+    report("conv1_fwd", x1, r1.permute(0, 2, 3, 1).detach(), 1e-2)
+    # ---- conv2 forward (implicit GEMM on tcgen05)
+    w2p = torch.empty(C, 9, C, dtype=torch.bfloat16, device=DEV)
+    L.call("permute3_bf16", w2, w2p, C, C, 9, 1)
+    x2 = torch.empty(B, T2, F2, C, dtype=torch.bfloat16, device=DEV)
+    L.call("conv3x3s2_fwd", x1, w2p, b2, len2, x2, B, T1, F1, C)
+    x1f = x1.float().permute(0, 3, 1, 2).requires_grad_(True)  # [B,C,T1,F1]
+    w2r = w2.to(torch.bfloat16).float().requires_grad_(True)
+    b2r = b2.clone().requires_grad_(True)
+    pre2 = Fn.conv2d(x1f, w2r, b2r, stride=2, padding=1)
+    r2 = Fn.relu(pre2) * tmask(T2, len2)[:, None, :, None]
+    report("conv2_fwd", x2, r2.permute(0, 2, 3, 1).detach(), 1e-2)
+    # ---- conv2 backward: dy (already gated by relu/mask like the engine produces it)
+    dy = (rnd(B, T2, F2, C, seed=7) * (x2.float() > 0)).to(torch.bfloat16)
+    pre2.backward(dy.float().permute(0, 3, 1, 2))
+    tmp = torch.empty(C, C, 9, device=DEV)
+    L.call("permute3_f32", w2, tmp, C, C, 9, 0, 0)
+    wd = torch.empty(C, 9, C, dtype=torch.bfloat16, device=DEV)
+    L.call("permute3_bf16", tmp, wd, C, C, 9, 1)
+    dx1 = torch.full((B, T1, F1, C), 7.0, dtype=torch.bfloat16, device=DEV)
+    L.call("conv3x3s2_bwd_data", dy, wd, x1, dx1, B, T1, F1, C)
+    ref_dx1 = x1f.grad.permute(0, 2, 3, 1) * (x1.float() > 0)
+    report("conv2_bwd_data", dx1, ref_dx1, 1.5e-2)
+    gw = torch.zeros(C, 9 * C, device=DEV)
+    L.call("conv3x3s2_bwd_weight", dy, x1, gw, B, T1, F1, C)
+    report("conv2_bwd_weight", gw.view(C, 9, C).permute(0, 2, 1).reshape(C, C, 3, 3), w2r.grad, 1e-2)
+    # ---- conv1 backward
+    r1.backward(dx1.float().permute(0, 3, 1, 2) * (x1.float().permute(0, 3, 1, 2) > 0))
+    dw1, db1 = torch.zeros(C, 9, device=DEV), torch.zeros(C, device=DEV)
+    L.call("subsample_conv1_bwd", mel, dx1, l32, dw1, db1, B, F, T, C)
+    report("conv1_bwd_dw", dw1.view(C, 1, 3, 3), w1r.grad, 1e-2)
+    report("conv1_bwd_db", db1, b1r.grad, 1e-2)

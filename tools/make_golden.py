@@ -72,3 +72,48 @@ if __name__ == "__main__":
                 n_heads=2)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+def gen_encoder_cuda_cfg():
+    """A configuration the CUDA path supports (head dim 64): weights = oracle.init_state_dict(seed) loaded into the
+    reference module, so the fixture only carries inputs, outputs and (sub-sampled) gradients."""
+    from oracle import conformer_oracle as O
+    cfgs = {
+        "enc_cuda_striding": dict(n_layers=2, d_model=128, n_heads=2, conv_kernel_size=9, subsampling_kind="striding",
+                                  subsampling_factor=4, subsampling_conv_channels=-1, seed=5),
+    }
+    for name, c in cfgs.items():
+        sd = O.init_state_dict(**c)
+        enc = rl.make_encoder(seed=0, feat_in=80, n_layers=c["n_layers"], d_model=c["d_model"], n_heads=c["n_heads"],
+                              conv_kernel_size=c["conv_kernel_size"], subsampling=c["subsampling_kind"],
+                              subsampling_factor=c["subsampling_factor"],
+                              subsampling_conv_channels=c["subsampling_conv_channels"], dropout=0.0,
+                              dropout_pre_encoder=0.0, dropout_emb=0.0, dropout_att=0.0)
+        enc.load_state_dict(sd)
+        g = torch.Generator().manual_seed(21)
+        x = torch.randn(3, 80, 131, generator=g)
+        length = torch.tensor([131, 97, 40])
+        for b in range(3):
+            x[b, :, length[b]:] = 0
+        enc.eval()
+        with torch.no_grad():
+            y_eval, ylen = enc(audio_signal=x, length=length)
+        enc.train()
+        y_train, _ = enc(audio_signal=x, length=length)
+        r = torch.randn(y_train.shape, generator=g)
+        loss = (y_train.float() * r).sum() / y_train.shape[0]
+        loss.backward()
+        grads = {}
+        for k, p in enc.named_parameters():
+            gflat = p.grad.detach().flatten()
+            grads[f"grad::{k}"] = (gflat if gflat.numel() <= 20000 else gflat[::97]).numpy()
+        bn = {f"bn::{k}": v.detach().numpy() for k, v in enc.state_dict().items() if "running_" in k}
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), x=x.numpy(), length=length.numpy(), y_eval=y_eval.numpy(),
+                            y_train=y_train.detach().numpy(), ylen=ylen.numpy(), loss=loss.detach().numpy(), r=r.numpy(),
+                            cfg=np.array(repr(c)), **grads, **bn)
+
+
+if __name__ == "__main__":
+    gen_encoder_cuda_cfg()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
