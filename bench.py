@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py — audio-seconds/s of the Conformer-ASR encoder hot path (mel front-end → subsampling → 18 Conformer
+layers, forward + backward + gradient all-reduce + AdamW) on N B200s.
+
+Workload = BASELINE.json configs[1]: Conformer-CTC-Large (18L, d=512, 8 heads, conv k=31, striding 4x), fwd+bwd,
+32 x 30 s synthetic 16 kHz utterances PER GPU (weak scaling), bf16 tensor-core arithmetic with fp32 master weights,
+dropout active (0.1 / 0.1 / att 0.1 as in examples/asr/conf/conformer/conformer_ctc_bpe.yaml), random-init weights.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # ours (N>1: launched under torchrun)
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference algorithm on the host CPU cores
+
+Prints ONE JSON line (contract in the task statement): value = whole-job audio-s/s with inputs resident in HBM;
+e2e = same metric through the public module API with pinned-host inputs (H2D each step) and a D2H loss read;
+roofline = achieved TFLOP/s of the dominant kernel family (tcgen05 GEMM) from CUDA events, vs the measured bf16 peak;
+cpu_baseline = the fp32 oracle port timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LARGE = dict(n_layers=18, d_model=512, n_heads=8, conv_kernel_size=31, subsampling_kind="striding", subsampling_factor=4)
+SECS, SR, PER_GPU_BATCH = 30.0, 16000, 32
+METRIC = "audio-sec/s Conformer-L fwd+bwd"
+
+
+def flops_fwd_bwd(B, T, d=512, L=18, h=8, dff=2048, k=31, C=512, F1=40, F2=20, T1=1501):
+    """dense-contraction MACs of the forward x 6 (fwd + bwd = 3 x 2 x MAC)."""
+    dk = d // h
+    sub = B * T1 * F1 * C * 9 + B * T * F2 * C * C * 9 + B * T * F2 * C * d
+    per_layer = (4 * B * T * d * dff + 4 * B * T * d * d + (2 * T - 1) * d * d + B * h * T * T * dk
+                 + B * h * T * (2 * T - 1) * dk + B * h * T * T * dk + 2 * B * T * d * d + B * T * d * k + B * T * d * d)
+    return 6.0 * (sub + L * per_layer)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return dict(tflops=float(j["bf16_tflops_sustained"]), hbm=float(j["hbm_gbs"]), src="measured")
+        except Exception:
+            pass
+    return dict(tflops=1590.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference / CPU arm
+def cpu_reference_step(O, sd, wav, wlen, cfg):
+    """One fwd+bwd of the reference algorithm (fp32 oracle port, PyTorch eager on the host cores)."""
+    params = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and "running" not in k) else v) for k, v in sd.items()}
+    mel, mlen = O.mel_frontend(wav, wlen)
+    y, _ = O.encoder_forward(params, mel, mlen, n_layers=cfg["n_layers"], d_model=cfg["d_model"], n_heads=cfg["n_heads"],
+                             subsampling_kind=cfg["subsampling_kind"], subsampling_factor=cfg["subsampling_factor"],
+                             training=True)
+    (y.float().pow(2).mean()).backward()
+
+
+def cpu_baseline(steps=2, warmup=1, batch=1):
+    from oracle import conformer_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = O.init_state_dict(seed=0, **LARGE)
+    wav, wlen = O.synthetic_waveforms(batch, SECS)
+    for _ in range(warmup):
+        cpu_reference_step(O, sd, wav, wlen, LARGE)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(O, sd, wav, wlen, LARGE)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": batch * SECS / dt, "unit": "audio-sec/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} steps of {batch}x{int(SECS)} s fwd+bwd (fp32 oracle port of the reference modules, PyTorch eager)",
+            "ms_per_step": dt * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(steps=max(1, args.steps), warmup=max(1, min(args.warmup, 1)), batch=1)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "audio-sec/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Conformer-CTC-Large 18L d512 h8 k31 striding4x fwd+bwd, 30 s utterances",
+                   "sample": "1x30 s per step on host CPU cores"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "audio-sec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def run_ours(args):
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from nemo_b200 import _lib as L
+    from nemo_b200.encoder import B200ConformerEncoder
+    from nemo_b200.parallel import FlatGradients
+    from nemo_b200.preprocessor import B200MelPreprocessor
+
+    B = args.batch
+    torch.manual_seed(0)  # identical replicas
+    enc = B200ConformerEncoder(feat_in=80, n_layers=LARGE["n_layers"], d_model=LARGE["d_model"], n_heads=LARGE["n_heads"],
+                               conv_kernel_size=LARGE["conv_kernel_size"], subsampling="striding", subsampling_factor=4,
+                               dropout=0.1, dropout_pre_encoder=0.1, dropout_emb=0.0, dropout_att=0.1).to(dev).train()
+    with torch.no_grad():
+        for lyr in enc.layers:
+            lyr.self_attn.pos_bias_u.normal_(0, 0.02)
+            lyr.self_attn.pos_bias_v.normal_(0, 0.02)
+    pre = B200MelPreprocessor(sample_rate=SR, window_size=0.025, window_stride=0.01, features=80, n_fft=512, dither=1e-5,
+                              pad_to=0).to(dev).train()
+    fg = FlatGradients(enc)
+    opt = torch.optim.AdamW(enc.parameters(), lr=1e-4, betas=(0.9, 0.98), weight_decay=1e-3, fused=True)
+    S = int(SECS * SR)
+    g = torch.Generator().manual_seed(1234 + rank)  # every rank its own shard of the global batch
+    wav_host = (torch.rand(B, S, generator=g) * 0.2 - 0.1).pin_memory()
+    len_host = torch.full((B,), S, dtype=torch.int64).pin_memory()
+    wav_dev, len_dev = wav_host.to(dev), len_host.to(dev)
+    T_enc = ((S // 160 + 1 - 1) // 2 + 1 - 1) // 2 + 1
+    proj = torch.randn(B, LARGE["d_model"], T_enc, device=dev) / (B * T_enc * LARGE["d_model"])
+    loss_scale = fg.loss_scale()
+
+    gemm_events = []
+    orig_gemm = L.gemm
+
+    def timed_gemm(A, Bm, M, N, K, *a, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_gemm(A, Bm, M, N, K, *a, **kw)
+        e1.record()
+        gemm_events.append((2.0 * M * N * K, e0, e1))
+
+    def step(wav, wlen, from_host):
+        if from_host:
+            wav, wlen = wav.to(dev, non_blocking=True), wlen.to(dev, non_blocking=True)
+        fg.zero()
+        mel, mlen = pre(input_signal=wav, length=wlen)
+        y, _ = enc(audio_signal=mel, length=mlen)
+        loss = (y * proj).sum() * loss_scale
+        loss.backward()
+        fg.finish()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, from_host, profile_gemm=False):
+        barrier()
+        if profile_gemm:
+            import nemo_b200.encoder as E
+            L.gemm = timed_gemm
+            E.L.gemm = timed_gemm
+        launches0 = L.lib.b2c_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            loss = step(wav_host if from_host else wav_dev, len_host if from_host else len_dev, from_host)
+            if from_host:
+                _ = loss.item()  # device→host read of the step's result
+        e1.record()
+        barrier()
+        if profile_gemm:
+            import nemo_b200.encoder as E
+            L.gemm = orig_gemm
+            E.L.gemm = orig_gemm
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), L.lib.b2c_launch_count() - launches0
+
+    for _ in range(max(args.warmup, 3)):
+        step(wav_dev, len_dev, False)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms, launches = timed(args.steps, False)
+    clk = clocks.stop() if rank == 0 else None
+    ms_e2e, _ = timed(args.steps, True)
+    # dominant-kernel roofline: every tcgen05 GEMM launch of one extra step bracketed by CUDA events
+    gemm_events.clear()
+    timed(1, False, profile_gemm=True)
+    torch.cuda.synchronize()
+    gf = sum(f for f, _, _ in gemm_events)
+    gms = sum(a.elapsed_time(b) for _, a, b in gemm_events)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        audio_s = world * B * SECS
+        value = audio_s * args.steps / (ms / 1e3)
+        e2e = audio_s * args.steps / (ms_e2e / 1e3)
+        achieved = gf / (gms / 1e3) / 1e12 if gms > 0 else 0.0
+        step_flops = flops_fwd_bwd(B, T_enc)
+        out = {
+            "metric": METRIC, "value": value, "unit": "audio-sec/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"Conformer-CTC-Large 18L d512 h8 k31 striding4x, {B}x30 s per GPU, mel+fwd+bwd+allreduce+AdamW",
+                       "global_batch": world * B, "parallelism": f"dp{world}", "dropout": "0.1/0.1/att0.1",
+                       "l2": "inputs+activations per step (>17 GB) exceed the 126 MB L2; no flush needed",
+                       "model_tflop_per_step_per_gpu": step_flops / 1e12,
+                       "model_tflops_achieved_per_gpu": step_flops / (ms / args.steps / 1e3) / 1e12},
+            "e2e": {"value": e2e, "unit": "audio-sec/s", "h2d_bytes_per_step": world * (wav_host.numel() * 4 + B * 8),
+                    "d2h_bytes_per_step": world * 4},
+            "gpu_launches": launches,
+            "clocks": clk,
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM family, all launches of one step)",
+                         "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                         "traffic": None, "peak_source": peaks["src"] + " bf16_tflops_sustained",
+                         "gemm_ms_per_step": gms, "gemm_share_of_step": gms / (ms / args.steps)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_baseline(steps=2, warmup=1, batch=1)
+            out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="utterances per GPU (default 32 = BASELINE config 2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

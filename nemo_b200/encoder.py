@@ -89,12 +89,12 @@ class _ConvSubsampling(nn.Module):  # ConvSubsampling, subsampling.py:62-383 ('s
             for _ in range(self._sampling_num - 1):
                 layers += [nn.Conv2d(conv_channels, conv_channels, 3, stride=2, padding=1, groups=conv_channels),
                            nn.Conv2d(conv_channels, conv_channels, 1), nn.ReLU(True)]
-        self.conv = nn.Sequential(*layers)
         f = feat_in
         for _ in range(self._sampling_num):
             f = (f + 2 - 3) // 2 + 1
         self._f_out = f
-        self.out = nn.Linear(conv_channels * f, feat_out)
+        self.out = nn.Linear(conv_channels * f, feat_out)  # registered before `conv`, like the reference
+        self.conv = nn.Sequential(*layers)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -172,7 +172,6 @@ class B200ConformerEncoder(nn.Module):
         if feat_out > 0 and feat_out != d_model: bad.append("feat_out projection")
         if d_model % n_heads or (d_model // n_heads) not in (64, 128): bad.append("head dim must be 64 or 128")
         if conv_kernel_size not in (31, 9, 5): bad.append(f"conv_kernel_size={conv_kernel_size}")
-        if dropout_emb not in (0, 0.0): bad.append("dropout_emb>0 (YAML recipes use 0.0)")
         if d_model % 64: bad.append("d_model % 64")
         if bad:
             raise NotImplementedError("B200ConformerEncoder (hot-path subset, SURVEY.md §8): unsupported " + ", ".join(bad))
@@ -185,6 +184,7 @@ class B200ConformerEncoder(nn.Module):
         self.att_context_size = [-1, -1]
         self.xscale = math.sqrt(d_model) if xscaling else None
         self.dropout, self.dropout_pre_encoder, self.dropout_att = dropout, dropout_pre_encoder, dropout_att
+        self.dropout_emb = dropout_emb
         self.pos_emb_max_len, self.max_audio_length = pos_emb_max_len, pos_emb_max_len
         # the reference all-reduces max length every forward (conformer_encoder.py:770-776): removed, the relative
         # position table is generated on the fly for the actual T (no host sync, no collective)
@@ -293,13 +293,18 @@ class B200ConformerEncoder(nn.Module):
             W[f"{i}.pw2"] = wc.get(f"{i}.pw2", [cv.pointwise_conv2.weight], lambda cv=cv: _cast(cv.pointwise_conv2.weight).view(d, d))
         return W
 
-    def _pos_table(self, T, dev):
+    def _pos_table(self, T, dev, p_emb=0.0, seed=0):
         key = (T, str(dev))
         if key not in self._pos_cache:
             p16 = _empty(2 * T - 1, self.d_model, dev=dev)
-            L.call("relpos_table", p16, None, T, self.d_model)
-            self._pos_cache = {key: p16}
-        return self._pos_cache[key]
+            p32 = _empty(2 * T - 1, self.d_model, dtype=F32, dev=dev)
+            L.call("relpos_table", p16, p32, T, self.d_model)
+            self._pos_cache = {key: (p16, p32)}
+        p16, p32 = self._pos_cache[key]
+        if p_emb > 0.0:  # dropout_emb on pos_emb (multi_head_attention.py:1097-1098), one mask per forward
+            p16 = _empty(2 * T - 1, self.d_model, dev=dev)
+            L.call("scale_drop_cast", p32, p16, p32.numel(), 1.0, p_emb, seed, self.n_layers * 16 + 1)
+        return p16
 
 
 def _gemm(A, Bm, M, N, K, mode, *, a_mn=0, b_mn=0, lda=None, ldb=None, **kw):
@@ -372,7 +377,7 @@ class _EncoderFn(torch.autograd.Function):
         x = _empty(M, d, dtype=F32, dev=dev)
         _gemm(xlast, W["out"], M, d, F2 * C, L.EPI_RESID_F32, out0=x, bias=pe.out.bias.detach(),
               alpha=enc.xscale or 1.0, seed=seed, drop_site=enc.n_layers * 16, drop_p=p_pre)
-        pos16 = enc._pos_table(T, dev)
+        pos16 = enc._pos_table(T, dev, enc.dropout_emb if training else 0.0, seed)
 
         # ---- conformer layers ---------------------------------------------------------------------------------
         layers_saved = []
@@ -456,6 +461,8 @@ class _EncoderFn(torch.autograd.Function):
     def backward(ctx, dout, _dlen):
         enc: B200ConformerEncoder = ctx.enc
         mt, W = ctx.meta, ctx.W
+        if dout is None:
+            return (None,) * (3 + mt["nparams"])
         B, T, M = mt["B"], mt["T"], mt["M"]
         seed, p_drop, p_pre, p_att, training = mt["seed"], mt["p_drop"], mt["p_pre"], mt["p_att"], mt["training"]
         d, H, dff, k = enc.d_model, enc.n_heads, enc.d_ff, enc.conv_kernel_size
@@ -465,14 +472,22 @@ class _EncoderFn(torch.autograd.Function):
         C, F2 = pe._conv_channels, pe._f_out
         names = [n for n, _ in enc.named_parameters()]
         plist = [p for _, p in enc.named_parameters()]
-        # one flat fp32 gradient buffer; per-parameter views
-        sizes = [p.numel() for p in plist]
-        flat = torch.zeros(sum(sizes), dtype=F32, device=dev)
-        G, off = {}, 0
-        for n, p, sz in zip(names, plist, sizes):
-            G[n] = flat[off:off + sz].view_as(p)
-            off += sz
-        enc._last_flat_grad = flat
+        # Gradients go into ONE flat fp32 buffer.  Default: a fresh zeroed buffer whose views are handed to autograd.
+        # With nemo_b200.parallel.FlatGradients attached, the kernels accumulate straight into its persistent buffer
+        # (`p.grad` already are views of it), autograd receives None, and each layer's slice is all-reduced as soon as
+        # its backward kernels are enqueued.
+        fg = enc.__dict__.get("_flat_grads")
+        G = {}
+        if fg is not None:
+            for n, p in zip(names, plist):
+                G[n] = fg.view(n).view_as(p) if n in fg.offsets else torch.zeros_like(p)
+        else:
+            sizes = [p.numel() for p in plist]
+            flat = torch.zeros(sum(sizes), dtype=F32, device=dev)
+            off = 0
+            for n, p, sz in zip(names, plist, sizes):
+                G[n] = flat[off:off + sz].view_as(p)
+                off += sz
 
         dr = dout.transpose(1, 2).contiguous().view(M, d).to(F32)
         t16 = _empty(M, d, dev=dev)
@@ -569,6 +584,8 @@ class _EncoderFn(torch.autograd.Function):
             # ---- feed_forward1
             ffn_bwd("feed_forward1", lyr.feed_forward1, "norm_feed_forward1", lyr.norm_feed_forward1, S_FF1_HID, None, 1.0,
                     0, 0.0)
+            if fg is not None:
+                fg.ready(*fg.span(pfx))
 
         # ---- pre_encode: xscale + dropout backward, out Linear, convolutions
         L.call("scale_drop_cast", dr, t16, M * d, enc.xscale or 1.0, p_pre, seed, enc.n_layers * 16)
@@ -592,5 +609,8 @@ class _EncoderFn(torch.autograd.Function):
                    G["pre_encode.conv.0.bias"], B, Fs[0], Ts[0], C)
         else:
             raise NotImplementedError("dw_striding backward is not built yet (forward / inference only)")
+        if fg is not None:
+            fg.ready(*fg.span("pre_encode."))
+            return (None,) * (3 + len(plist))
         grads = [G[n] if p.requires_grad else None for n, p in zip(names, plist)]
         return (None, None, None, *grads)

@@ -1,0 +1,81 @@
+"""Data-parallel plumbing for the encoder hot path: the utterance batch is sharded across ranks (one process per GPU,
+weights replicated) and the ONLY collective is the gradient sum all-reduce — the reference's
+Lightning `DDPStrategy` reducer (examples/asr/conf/conformer/conformer_ctc_bpe.yaml:201) re-thought for this engine:
+
+* the backward kernels write every parameter gradient straight into ONE flat fp32 buffer (`p.grad` are views of it),
+  so there is no bucket packing pass at all;
+* as soon as a layer's backward kernels are enqueued, its contiguous slice of the flat buffer is all-reduced with
+  `async_op=True` — NCCL (NVLS on the NVSwitch domain) runs on its own stream while the remaining layers' backward
+  kernels keep the SMs busy;
+* the reference's per-forward `all_reduce(MAX)` of the sequence length (conformer_encoder.py:770-776) and SyncBatchNorm
+  (`trainer.sync_batchnorm`) are deliberately NOT reproduced (north_star: gradient all-reduce is the sole collective).
+  Multi-GPU results therefore equal a reference DDP run with `sync_batchnorm=false`.
+
+Works with any torch.distributed backend (NCCL on GPUs; gloo in the CPU tests)."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class FlatGradients:
+    """Owns the flat gradient buffer of a module and the layer-wise overlapped all-reduce."""
+
+    def __init__(self, module: torch.nn.Module, process_group=None, grad_dtype=torch.float32):
+        self.module = module
+        self.group = process_group
+        params = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        self.names = [n for n, _ in params]
+        self.sizes = [p.numel() for _, p in params]
+        dev = params[0][1].device
+        self.flat = torch.zeros(sum(self.sizes), dtype=grad_dtype, device=dev)
+        self.offsets = {}
+        off = 0
+        for (n, p), sz in zip(params, self.sizes):
+            self.offsets[n] = (off, off + sz)
+            p.grad = self.flat[off:off + sz].view_as(p)
+            off += sz
+        self._handles: List = []
+        self._reduced_upto: Optional[int] = None
+        module.__dict__["_flat_grads"] = self  # encoder backward writes here and calls `ready(lo, hi)`
+
+    # ---- called by the backward orchestration ------------------------------------------------------------------
+    def view(self, name: str) -> torch.Tensor:
+        lo, hi = self.offsets[name]
+        return self.flat[lo:hi]
+
+    def span(self, prefix: str):
+        los = [v[0] for k, v in self.offsets.items() if k.startswith(prefix)]
+        his = [v[1] for k, v in self.offsets.items() if k.startswith(prefix)]
+        return (min(los), max(his)) if los else None
+
+    def ready(self, lo: int, hi: int):
+        """Gradients in flat[lo:hi] are final (their kernels are enqueued on the current stream)."""
+        if self._world() > 1 and hi > lo:
+            self._handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    # ---- called by the training loop ---------------------------------------------------------------------------
+    def _world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def zero(self):
+        self.flat.zero_()
+
+    def finish(self):
+        """Wait for the outstanding all-reduces (the current stream waits; no host sync for NCCL)."""
+        for h in self._handles:
+            h.wait()
+        self._handles.clear()
+
+    def loss_scale(self) -> float:
+        """Scale the local loss by this so the summed gradients equal the global-batch mean."""
+        return 1.0 / self._world()
+
+
+def shard_batch(n_items: int, rank: int, world: int):
+    """Contiguous, near-even shard [lo, hi) of the utterance batch for `rank` (no data-path collective)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)

@@ -1,0 +1,131 @@
+"""CPU tests of the host-side logic: drop-in boundary (constructor kwargs, state_dict layout, error behaviour),
+data-parallel gradient plumbing (gloo, world_size 2) and the benchmark's work model.  No CUDA compute."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from nemo_b200.encoder import B200ConformerEncoder
+from nemo_b200.parallel import FlatGradients, shard_batch
+from nemo_b200.preprocessor import B200MelPreprocessor, slaney_mel_filterbank
+from oracle import conformer_oracle as O
+from oracle import ref_loader as rl
+
+needs_ref = pytest.mark.skipif(not rl.available(), reason="/root/reference not present")
+
+
+def test_encoder_state_dict_layout_matches_oracle_init():
+    for kind, fac, ch in (("striding", 4, -1), ("dw_striding", 8, 64)):
+        enc = B200ConformerEncoder(feat_in=80, n_layers=2, d_model=128, n_heads=2, conv_kernel_size=9, subsampling=kind,
+                                   subsampling_factor=fac, subsampling_conv_channels=ch)
+        sd = O.init_state_dict(n_layers=2, d_model=128, n_heads=2, conv_kernel_size=9, subsampling_kind=kind,
+                               subsampling_factor=fac, subsampling_conv_channels=ch)
+        res = enc.load_state_dict(sd, strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+        for k, v in enc.state_dict().items():
+            assert tuple(v.shape) == tuple(sd[k].shape), k
+
+
+@needs_ref
+def test_encoder_is_a_drop_in_for_the_reference_module():
+    ref = rl.make_encoder(feat_in=80, n_layers=2, d_model=128, n_heads=2, conv_kernel_size=31, dropout=0.1, dropout_att=0.1)
+    new = B200ConformerEncoder.from_reference(ref)
+    assert list(new.state_dict().keys()) == list(ref.state_dict().keys())  # same keys, same order
+    for (k, a), (_, b) in zip(new.state_dict().items(), ref.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert (new._feat_out, new.d_model, new.subsampling_factor, len(new.layers)) == (ref._feat_out, ref.d_model, ref.subsampling_factor, len(ref.layers))
+    assert new.dropout == 0.1 and new.dropout_att == 0.1 and hasattr(new, "pre_encode")
+    # reference error behaviour (conformer_encoder.py:569-573) and no silent CPU fallback
+    with pytest.raises(ValueError):
+        new(audio_signal=torch.zeros(1, 79, 50), length=torch.tensor([50]))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        new(audio_signal=torch.zeros(1, 80, 50), length=torch.tensor([50]))
+
+
+def test_encoder_rejects_configurations_outside_the_hot_path():
+    base = dict(feat_in=80, n_layers=1, d_model=128, n_heads=2)
+    for bad in (dict(self_attention_model="abs_pos"), dict(subsampling="vggnet"), dict(conv_norm_type="layer_norm"),
+                dict(att_context_size=[64, 0]), dict(n_heads=4), dict(causal_downsampling=True),
+                dict(stochastic_depth_drop_prob=0.1), dict(reduction="pooling", reduction_factor=2, reduction_position=0)):
+        with pytest.raises(NotImplementedError):
+            B200ConformerEncoder(**{**base, **bad})
+    enc = B200ConformerEncoder(**base)
+    with pytest.raises(NotImplementedError):
+        enc.cache_aware_stream_step()
+    with pytest.raises(NotImplementedError):
+        enc(audio_signal=torch.zeros(1, 80, 10), length=None, cache_last_channel=torch.zeros(1))
+
+
+def test_preprocessor_boundary(golden_dir):
+    pre = B200MelPreprocessor(window_size=0.025, window_stride=0.01, features=80, n_fft=512, pad_to=0)
+    assert list(pre.state_dict().keys()) == ["featurizer.window", "featurizer.fb"]
+    z = np.load(os.path.join(golden_dir, "mel.npz"))  # buffers of the reference FilterbankFeatures
+    assert np.array_equal(pre.featurizer.fb[0].numpy(), z["fb"])
+    assert np.array_equal(pre.featurizer.window.numpy(), z["window"])
+    assert pre.filter_banks.shape == (1, 80, 257) and pre._sample_rate == 16000
+    assert (pre.featurizer.dither, pre.featurizer.pad_to) == (1e-5, 0)
+    with pytest.raises(ValueError):
+        B200MelPreprocessor(window_size=0.025, n_window_size=400)
+    with pytest.raises(NotImplementedError):
+        B200MelPreprocessor(window_size=0.025, window_stride=0.01, n_fft=1024)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pre(input_signal=torch.zeros(1, 1600), length=torch.tensor([1600]))
+    assert np.array_equal(slaney_mel_filterbank(16000, 512, 80), O.slaney_mel_filterbank())
+
+
+def test_shard_batch_partitions_the_global_batch():
+    for n, w in ((32, 1), (32, 8), (64, 4), (16, 8), (10, 3)):
+        spans = [shard_batch(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    enc = B200ConformerEncoder(feat_in=80, n_layers=2, d_model=128, n_heads=2, conv_kernel_size=9)
+    fg = FlatGradients(enc)
+    assert all(p.grad.data_ptr() >= fg.flat.data_ptr() for p in enc.parameters())
+    # emulate the backward orchestration: last layer first, each layer's slice all-reduced as soon as it is "ready"
+    g = torch.Generator().manual_seed(100 + rank)
+    local = torch.randn(fg.flat.numel(), generator=g)
+    for pfx in ("layers.1.", "layers.0.", "pre_encode."):
+        lo, hi = fg.span(pfx)
+        fg.flat[lo:hi] += local[lo:hi]
+        fg.ready(lo, hi)
+    fg.finish()
+    expect = sum(torch.randn(fg.flat.numel(), generator=torch.Generator().manual_seed(100 + r)) for r in range(world))
+    ok = torch.allclose(fg.flat, expect, atol=1e-6)
+    covered = sorted(fg.span(p) for p in ("pre_encode.", "layers.0.", "layers.1."))
+    contiguous = covered[0][0] == 0 and covered[-1][1] == fg.flat.numel() and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
+    q.put((rank, bool(ok), bool(contiguous), fg.loss_scale()))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, contiguous, scale in res:
+        assert ok and contiguous and scale == 0.5, (rank, ok, contiguous, scale)
+
+
+def test_bench_work_model_matches_baseline_md():
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    assert abs(bench.flops_fwd_bwd(32, 751) / 1e12 - 27.34) < 0.02  # 27.34 TFLOP / step at 32x30 s
+    assert abs(bench.flops_fwd_bwd(1, 751) / 6 / 1e9 * 2 - 298.47) < 12  # ~298.5 GFLOP fwd for 1x30 s (pos term is batch-indep.)

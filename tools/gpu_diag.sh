@@ -11,7 +11,7 @@ i=0
 for g in "${groups[@]}"; do
   i=$((i+1))
   echo "=== group $i: $g" | tee -a gpurun_out/diag_summary.txt
-  timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -q -s -k "$g" > "gpurun_out/diag_$i.log" 2>&1
+  timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_encoder_gpu.py -m gpu -q -s -k "$g" > "gpurun_out/diag_$i.log" 2>&1
   rc=$?
   echo "rc=$rc" | tee -a gpurun_out/diag_summary.txt
   grep -E "^\[|passed|failed|error|Error|timeout|rel err|assert" "gpurun_out/diag_$i.log" | tail -60 >> gpurun_out/diag_summary.txt
