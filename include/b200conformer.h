@@ -61,7 +61,7 @@ typedef struct {
   float alpha;
   unsigned long long seed; /* dropout: Philox key */
   unsigned int drop_site;  /* dropout: site id (layer*16 + site) */
-  unsigned int drop_keep;  /* dropout: keep threshold = (1-p)*2^32, 0 = no dropout */
+  unsigned int drop_keep;  /* dropout: 16-bit keep threshold = round((1-p)*65536), 0 = no dropout */
   float drop_scale;        /* 1/(1-p) */
 } b2c_epilogue;
 
@@ -174,6 +174,11 @@ int b2c_conv3x3s2_bwd_weight(const void* dy_bf16, const void* x_bf16, float* dw,
  * subsampling.py:142-215). */
 int b2c_dwconv3x3s2_fwd(const void* in_bf16, const float* w, const float* bias, const int32_t* len_out, void* out_bf16,
                         int B, int T1, int F1, int C, void* stream);
+
+/* backward of the depthwise stage: dx = relu'(x) * conv_transpose(dy) (dy rows t2 >= len_out are treated as zero),
+ * dw [C,9] +=, dbias [C] += */
+int b2c_dwconv3x3s2_bwd(const void* dy_bf16, const void* x_bf16, const float* w, const int32_t* len_out, void* dx_bf16,
+                        float* dw, float* dbias, int B, int T1, int F1, int C, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ misc
  * relative positional table rows = positions T-1 … -(T-1) (multi_head_attention.py:1007-1020,1056-1100) */

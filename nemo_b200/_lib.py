@@ -102,7 +102,7 @@ def call(name: str, *args):
 
 
 def drop_keep(p: float) -> int:
-    return 0 if p <= 0.0 else int((1.0 - p) * 4294967296.0)
+    return 0 if p <= 0.0 else int((1.0 - p) * 65536.0 + 0.5)
 
 
 def gemm(A, B, M, N, K, lda, ldb, a_mn, b_mn, mode, *, out0, out1=None, aux=None, bias=None, lengths=None, ldo=None,

@@ -155,7 +155,8 @@ __device__ __forceinline__ void score_tile(float (&s)[8][4], const uint32_t (&qu
 }
 
 __device__ __forceinline__ bool attn_keep(const AttnArgs& a, int b, int h, int i, int j) {
-  const uint64_t idx = ((uint64_t)((b * a.H + h) * (int64_t)a.T + i)) * (uint64_t)a.T + (uint64_t)j;
+  // row pitch rounded up to even so the (j, j+1) pairs a thread owns share one hash
+  const uint64_t idx = ((uint64_t)((b * a.H + h) * (int64_t)a.T + i)) * (uint64_t)((a.T + 1) & ~1) + (uint64_t)j;
   return dropout_keep(a.seed, a.site, idx, a.drop_keep);
 }
 
@@ -542,10 +543,12 @@ relpos_attn_bwd_kv_kernel(const AttnArgs a, const bf16* __restrict__ dctx, const
 }
 
 // =============================================================================================== backward (position side)
-// CTA owns 64 relative-position rows r of one head: dpos[r, h*DK + :] = sum_b sum_i dS[b,h,i, i-(T-1)+r] * bf16(q_{b,i}+v)
+// CTA owns 64 relative-position rows r of one head for a chunk of the batch:
+//   dpos[r, h*DK + :] += sum_{b in chunk} sum_i dS[b,h,i, i-(T-1)+r] * bf16(q_{b,i}+v)      (vector reductions at the end)
 template <int DK>
 __global__ void __launch_bounds__(128)
-relpos_attn_bwd_pos_kernel(const AttnArgs a, const bf16* __restrict__ ws_ds, float* __restrict__ dpos, int Tp) {
+relpos_attn_bwd_pos_kernel(const AttnArgs a, const bf16* __restrict__ ws_ds, float* __restrict__ dpos, int Tp,
+                           int b_per_cta) {
   constexpr int P = DK + 8;
   constexpr int PX = 64 + 8;
   extern __shared__ __align__(16) uint8_t smraw[];
@@ -560,7 +563,8 @@ relpos_attn_bwd_pos_kernel(const AttnArgs a, const bf16* __restrict__ ws_ds, flo
   for (int nt = 0; nt < DK / 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
   // rows i that can pair with r in [r0, r0+64): j = i - (T-1) + r in [0, T)  →  i in [T-1-r0-63, 2T-2-r0]
   const int i_lo = max(0, T - 1 - (r0 + 63)), i_hi = min(T - 1, 2 * T - 2 - r0);
-  for (int b = 0; b < a.B; ++b) {
+  const int b_lo = blockIdx.z * b_per_cta, b_hi = min(a.B, b_lo + b_per_cta);
+  for (int b = b_lo; b < b_hi; ++b) {
     const int len = a.lengths ? min(a.lengths[b], T) : T;
     const int hi = min(i_hi, len - 1);
     const bf16* qb = a.qkv + (size_t)b * T * ld + h * DK;
@@ -604,10 +608,7 @@ relpos_attn_bwd_pos_kernel(const AttnArgs a, const bf16* __restrict__ ws_ds, flo
     if (r < R) {
       float* op = dpos + (size_t)r * a.d + h * DK;
 #pragma unroll
-      for (int nt = 0; nt < DK / 8; ++nt) {
-        op[nt * 8 + 2 * c] += acc[nt][rr * 2];
-        op[nt * 8 + 2 * c + 1] += acc[nt][rr * 2 + 1];
-      }
+      for (int nt = 0; nt < DK / 8; ++nt) red_add_v2(op + nt * 8 + 2 * c, acc[nt][rr * 2], acc[nt][rr * 2 + 1]);
     }
   }
 }
@@ -625,7 +626,7 @@ static int fill_args(AttnArgs& a, const void* qkv, const void* pos, const float*
   a.drop_p = drop_p; a.seed = seed; a.site = site;
   a.drop_keep = 0; a.drop_scale = 1.f;
   if (drop_p > 0.f) {
-    a.drop_keep = (unsigned int)((1.0 - (double)drop_p) * 4294967296.0);
+    a.drop_keep = (unsigned int)((1.0 - (double)drop_p) * 65536.0 + 0.5);
     a.drop_scale = 1.f / (1.f - drop_p);
   }
   return B2C_OK;
@@ -665,7 +666,9 @@ static int launch_bwd(const AttnArgs& a, const bf16* ctx, const bf16* dctx, cons
   B2C_LAUNCH_CHECK();
   relpos_attn_bwd_kv_kernel<DK><<<dim3(qt, a.H, a.B), 128, smem2, st>>>(a, dctx, ws_ds, ws_p, dqkv, Tp);
   B2C_LAUNCH_CHECK();
-  relpos_attn_bwd_pos_kernel<DK><<<dim3((2 * a.T - 1 + 63) / 64, a.H), 128, smem3, st>>>(a, ws_ds, dpos, Tp);
+  const int b_per_cta = 2;
+  relpos_attn_bwd_pos_kernel<DK><<<dim3((2 * a.T - 1 + 63) / 64, a.H, (a.B + b_per_cta - 1) / b_per_cta), 128, smem3, st>>>(
+      a, ws_ds, dpos, Tp, b_per_cta);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
 }

@@ -49,12 +49,18 @@ typedef __nv_bfloat162 bf162;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+// sigmoid via one MUFU op: sigma(x) = 0.5 * tanh(0.5 x) + 0.5  (tanh.approx.f32: abs err ~5e-4 << bf16 resolution)
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
+__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
 // d/dx silu(x) = s(1 + x(1-s))
 __device__ __forceinline__ float dsilu_f(float x) {
   float s = sigmoid_f(x);
-  return s * (1.f + x * (1.f - s));
+  return s * fmaf(x, 1.f - s, 1.f);
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -209,16 +215,26 @@ __device__ __forceinline__ uint4 philox4(uint32_t c0, uint32_t c1, uint32_t c2, 
   }
   return make_uint4(c0, c1, c2, c3);
 }
-// Dropout keep decision for element `idx` of dropout site `site`: a stateless counter hash (two rounds of the
-// lowbias32 integer finaliser) so forward and backward regenerate identical masks.  keep_thresh = (1-p)*2^32.
+// Dropout: stateless counter hash so forward and backward regenerate identical masks.  One 32-bit hash serves the
+// element PAIR (idx & ~1, idx | 1): low / high 16 bits are compared with keep16 = round((1-p) * 65536).
 __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
 }
-__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t site, uint64_t idx, uint32_t keep_thresh) {
-  uint32_t h = hash32((uint32_t)idx ^ (uint32_t)seed);
-  h = hash32(h ^ (uint32_t)(idx >> 32) ^ (site * 0x9E3779B9U) ^ (uint32_t)(seed >> 32));
-  return h < keep_thresh;
+__device__ __forceinline__ uint32_t dropout_hash(uint64_t seed, uint32_t site, uint64_t pair_idx) {
+  return hash32((uint32_t)pair_idx ^ (uint32_t)seed ^ ((uint32_t)(pair_idx >> 32) * 0x9E3779B1U) ^ (site * 0x85EBCA77U) ^
+                __funnelshift_l((uint32_t)(seed >> 32), (uint32_t)(seed >> 32), 13));
+}
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t site, uint64_t idx, uint32_t keep16) {
+  const uint32_t h = dropout_hash(seed, site, idx >> 1);
+  return ((idx & 1) ? (h >> 16) : (h & 0xFFFFu)) < keep16;
+}
+// vector fp32 reduction to global memory (sm_90+): out[0..3] += v
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 #endif  // __CUDACC__
 

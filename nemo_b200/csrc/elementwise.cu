@@ -6,8 +6,9 @@
 
 namespace b2c {
 
-constexpr int kMaxVec = 8;  // d <= 1024 (8 float4 per lane)
+constexpr int kMaxVecLimit = 8;  // d <= 1024 (8 float4 per lane)
 
+template <int kMaxVec>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      bf16* __restrict__ y16, float* __restrict__ y32, float* __restrict__ mean_out,
@@ -63,7 +64,7 @@ struct DropArgs {
 };
 
 // rows handled per warp are strided so each warp keeps per-column dgamma/dbeta partials in registers
-template <bool DY_BF16>
+template <bool DY_BF16, int kMaxVec>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dr,
@@ -161,34 +162,47 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, 
   }
 }
 
-// out[n] += sum_m in[m, n]; CTA = 64 columns x row-chunk
+// out[n] += sum_m in[m, n]; CTA = 256 columns (32 lanes x 8 bf16 = 16 B per lane) x row-chunk, 4 rows in flight per warp
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const bf16* __restrict__ in, float* __restrict__ out, int M, int N, int ld, int rows_per_cta) {
-  __shared__ float red[8][64];
+  __shared__ float red[8][256];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int n = blockIdx.x * 64 + lane * 2;
+  const int n = blockIdx.x * 256 + lane * 8;
   const int r0 = blockIdx.y * rows_per_cta, r1 = min(M, r0 + rows_per_cta);
-  float a = 0.f, b = 0.f;
-  if (n < N) {
-    for (int m = r0 + w; m < r1; m += 8) {
-      if (n + 1 < N) {
-        float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(in + (size_t)m * ld + n));
-        a += v.x; b += v.y;
-      } else {
-        a += __bfloat162float(in[(size_t)m * ld + n]);
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  const bool vec = (n + 8 <= N) && (ld % 8 == 0);
+  if (vec) {
+    int m = r0 + w;
+    for (; m + 24 < r1; m += 32) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(in + (size_t)(m + 8 * k) * ld + n);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float2 p0 = unpack_bf16(u[k].x), p1 = unpack_bf16(u[k].y), p2 = unpack_bf16(u[k].z), p3 = unpack_bf16(u[k].w);
+        a[0] += p0.x; a[1] += p0.y; a[2] += p1.x; a[3] += p1.y; a[4] += p2.x; a[5] += p2.y; a[6] += p3.x; a[7] += p3.y;
       }
     }
+    for (; m < r1; m += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(in + (size_t)m * ld + n);
+      float2 p0 = unpack_bf16(u.x), p1 = unpack_bf16(u.y), p2 = unpack_bf16(u.z), p3 = unpack_bf16(u.w);
+      a[0] += p0.x; a[1] += p0.y; a[2] += p1.x; a[3] += p1.y; a[4] += p2.x; a[5] += p2.y; a[6] += p3.x; a[7] += p3.y;
+    }
+  } else {
+    for (int m = r0 + w; m < r1; m += 8)
+      for (int j = 0; j < 8; ++j)
+        if (n + j < N) a[j] += __bfloat162float(in[(size_t)m * ld + n + j]);
   }
-  red[w][lane * 2] = a;
-  red[w][lane * 2 + 1] = b;
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
-    const int nn = blockIdx.x * 64 + threadIdx.x;
-    if (nn < N) atomicAdd(out + nn, s);
-  }
+  for (int j = 0; j < 8; ++j) red[w][lane * 8 + j] = a[j];
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i][threadIdx.x];
+  const int nn = blockIdx.x * 256 + threadIdx.x;
+  if (nn < N) atomicAdd(out + nn, sum);
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n, float scale) {
@@ -287,11 +301,15 @@ using namespace b2c;
 
 extern "C" int b2c_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
                                  float* mean, float* rstd, int M, int d, void* stream) {
-  B2C_REQUIRE(d % 4 == 0 && d <= kMaxVec * 128, "layernorm: d=%d unsupported (need d%%4==0, d<=1024)", d);
+  B2C_REQUIRE(d % 4 == 0 && d <= kMaxVecLimit * 128, "layernorm: d=%d unsupported (need d%%4==0, d<=1024)", d);
   B2C_REQUIRE(M > 0, "layernorm: M=%d", M);
   const int wpb = 8;
-  layernorm_fwd_kernel<<<(M + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
-      x, gamma, beta, reinterpret_cast<bf16*>(y_bf16), y_f32, mean, rstd, M, d);
+  const dim3 grid((M + wpb - 1) / wpb);
+  bf16* y16 = reinterpret_cast<bf16*>(y_bf16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d <= 256) layernorm_fwd_kernel<2><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y16, y_f32, mean, rstd, M, d);
+  else if (d <= 512) layernorm_fwd_kernel<4><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y16, y_f32, mean, rstd, M, d);
+  else layernorm_fwd_kernel<8><<<grid, wpb * 32, 0, st>>>(x, gamma, beta, y16, y_f32, mean, rstd, M, d);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
 }
@@ -300,10 +318,10 @@ extern "C" int b2c_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x,
                                  const float* rstd, float* dr, int accumulate, float* dgamma, float* dbeta,
                                  void* next_bf16, float next_scale, float drop_p, unsigned long long seed,
                                  unsigned int site, int M, int d, void* stream) {
-  B2C_REQUIRE(d % 4 == 0 && d <= kMaxVec * 128, "layernorm_bwd: d=%d unsupported", d);
+  B2C_REQUIRE(d % 4 == 0 && d <= kMaxVecLimit * 128, "layernorm_bwd: d=%d unsupported", d);
   DropArgs da{seed, site, 0u, 1.f};
   if (drop_p > 0.f) {
-    da.keep = (unsigned int)((1.0 - (double)drop_p) * 4294967296.0);
+    da.keep = (unsigned int)((1.0 - (double)drop_p) * 65536.0 + 0.5);
     da.scale = 1.f / (1.f - drop_p);
   }
   const int wpb = 8;
@@ -311,19 +329,24 @@ extern "C" int b2c_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x,
   const int cap = num_sms() * 4;
   if (grid > cap) grid = cap;
   const size_t smem = 2 * (size_t)d * sizeof(float);
-  if (dy_is_bf16)
-    layernorm_bwd_kernel<true><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(
-        dy, x, gamma, mean, rstd, dr, accumulate, dgamma, dbeta, reinterpret_cast<bf16*>(next_bf16), next_scale, da, M, d);
-  else
-    layernorm_bwd_kernel<false><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(
-        dy, x, gamma, mean, rstd, dr, accumulate, dgamma, dbeta, reinterpret_cast<bf16*>(next_bf16), next_scale, da, M, d);
+  bf16* nx = reinterpret_cast<bf16*>(next_bf16);
+  cudaStream_t st = (cudaStream_t)stream;
+#define B2C_LN_BWD(BF, NV)                                                                                          \
+  layernorm_bwd_kernel<BF, NV><<<grid, wpb * 32, smem, st>>>(dy, x, gamma, mean, rstd, dr, accumulate, dgamma, dbeta, nx, \
+                                                            next_scale, da, M, d)
+  if (dy_is_bf16) {
+    if (d <= 256) B2C_LN_BWD(true, 2); else if (d <= 512) B2C_LN_BWD(true, 4); else B2C_LN_BWD(true, 8);
+  } else {
+    if (d <= 256) B2C_LN_BWD(false, 2); else if (d <= 512) B2C_LN_BWD(false, 4); else B2C_LN_BWD(false, 8);
+  }
+#undef B2C_LN_BWD
   B2C_LAUNCH_CHECK();
   return B2C_OK;
 }
 
 extern "C" int b2c_colsum_bf16(const void* in_bf16, float* out, int M, int N, int ld, void* stream) {
   B2C_REQUIRE(M > 0 && N > 0 && ld % 2 == 0, "colsum: bad args");
-  const int col_blocks = (N + 63) / 64;
+  const int col_blocks = (N + 255) / 256;
   int row_blocks = (num_sms() * 4 + col_blocks - 1) / col_blocks;
   if (row_blocks < 1) row_blocks = 1;
   int rows_per_cta = (M + row_blocks - 1) / row_blocks;
@@ -349,7 +372,7 @@ extern "C" int b2c_scale_drop_cast(const float* in, void* out_bf16, long long n,
   B2C_REQUIRE(n > 0, "scale_drop_cast: n=%lld", n);
   DropArgs da{seed, site, 0u, 1.f};
   if (drop_p > 0.f) {
-    da.keep = (unsigned int)((1.0 - (double)drop_p) * 4294967296.0);
+    da.keep = (unsigned int)((1.0 - (double)drop_p) * 65536.0 + 0.5);
     da.scale = 1.f / (1.f - drop_p);
   }
   scale_drop_cast_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(

@@ -24,7 +24,8 @@ namespace b2c {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int kNumThreads = 256;
+constexpr int kNumThreads = 384;  // 4 role warps + 8 epilogue warps
+constexpr int kEpiWarps = 8;
 
 // Implicit-GEMM geometry of the 3x3 stride-2 subsampling convolution (no im2col is ever materialised: the
 // A tiles are gathered by 4-D TMA boxes, strided for the forward / weight-gradient, shifted for the data-gradient).
@@ -57,7 +58,31 @@ struct SmemLayout {
 };
 
 // ---------------------------------------------------------------- epilogue
-// Each call handles one accumulator row `m`, 32 consecutive columns starting at n0.
+// Each call handles one accumulator row `m`, 32 consecutive columns starting at n0 (n0 % 32 == 0).
+__device__ __forceinline__ void store_bf16x32(bf16* o, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 8)
+    *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
+                                                  pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+}
+__device__ __forceinline__ void load_bf16x32(const bf16* p, float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p + j);
+    float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    v[j] = a.x; v[j + 1] = a.y; v[j + 2] = b.x; v[j + 3] = b.y; v[j + 4] = c.x; v[j + 5] = c.y; v[j + 6] = d.x; v[j + 7] = d.y;
+  }
+}
+// v[j] = keep ? v[j] * scale : 0 for the 32 elements idx0 .. idx0+31 (idx0 even): one hash per element pair
+__device__ __forceinline__ void dropout32(float (&v)[32], const b2c_epilogue& e, uint64_t idx0) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const uint32_t h = dropout_hash(e.seed, e.drop_site, (idx0 + j) >> 1);
+    v[j] = ((h & 0xFFFFu) < e.drop_keep) ? v[j] * e.drop_scale : 0.f;
+    v[j + 1] = ((h >> 16) < e.drop_keep) ? v[j + 1] * e.drop_scale : 0.f;
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n0, int M, int N, const uint32_t (&acc)[32],
                                              bool atomic) {
@@ -66,11 +91,11 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-  if (MODE != B2C_EPI_ACCUM_F32 && e.bias != nullptr) {
+  if (MODE != B2C_EPI_ACCUM_F32 && MODE != B2C_EPI_RELU_BWD && MODE != B2C_EPI_DSILU && e.bias != nullptr) {
     if (full) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        float4 b = *reinterpret_cast<const float4*>(e.bias + n0 + j);
+        const float4 b = *reinterpret_cast<const float4*>(e.bias + n0 + j);
         v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
       }
     } else {
@@ -78,47 +103,31 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
     }
   }
   const size_t ldo = (size_t)e.ldo;
+  const uint64_t didx = (uint64_t)m * (uint64_t)N + (uint64_t)n0;  // dropout element index (N even)
 
   if (MODE == B2C_EPI_BF16) {
     // out_bf16[m, n] = bf16(acc + bias)
     bf16* o = reinterpret_cast<bf16*>(e.out0) + (size_t)m * ldo + n0;
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        uint4 p = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]), pack_bf16(v[j + 4], v[j + 5]),
-                             pack_bf16(v[j + 6], v[j + 7]));
-        *reinterpret_cast<uint4*>(o + j) = p;
-      }
-    } else {
-      for (int j = 0; j < 32 && n0 + j < N; ++j) o[j] = __float2bfloat16_rn(v[j]);
-    }
+    if (full) store_bf16x32(o, v);
+    else for (int j = 0; j < 32 && n0 + j < N; ++j) o[j] = __float2bfloat16_rn(v[j]);
   } else if (MODE == B2C_EPI_SILU) {
-    // z = bf16(acc+bias) → out0 ; h = bf16(silu(z)) [* dropout] → out1   (conformer_modules.py:383-385)
+    // z = bf16(acc+bias) → out0 ; h = bf16(dropout(silu(z))) → out1   (conformer_modules.py:383-385)
     bf16* oz = reinterpret_cast<bf16*>(e.out0) + (size_t)m * ldo + n0;
     bf16* oh = reinterpret_cast<bf16*>(e.out1) + (size_t)m * ldo + n0;
     float h[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      float z = bf16_round(v[j]);
-      v[j] = z;
-      h[j] = silu_f(z);
+      v[j] = bf16_round(v[j]);
+      h[j] = silu_f(v[j]);
     }
     if (e.drop_keep != 0) {
-      const float inv = e.drop_scale;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        uint64_t idx = (uint64_t)m * (uint64_t)N + (uint64_t)(n0 + j);
-        h[j] = dropout_keep(e.seed, e.drop_site, idx, e.drop_keep) ? bf16_round(h[j]) * inv : 0.f;
-      }
+      for (int j = 0; j < 32; ++j) h[j] = bf16_round(h[j]);
+      dropout32(h, e, didx);
     }
     if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        *reinterpret_cast<uint4*>(oz + j) = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
-                                                       pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
-        *reinterpret_cast<uint4*>(oh + j) = make_uint4(pack_bf16(h[j], h[j + 1]), pack_bf16(h[j + 2], h[j + 3]),
-                                                       pack_bf16(h[j + 4], h[j + 5]), pack_bf16(h[j + 6], h[j + 7]));
-      }
+      store_bf16x32(oz, v);
+      store_bf16x32(oh, h);
     } else {
       for (int j = 0; j < 32 && n0 + j < N; ++j) {
         oz[j] = __float2bfloat16_rn(v[j]);
@@ -131,20 +140,13 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
     const float* r = e.aux ? reinterpret_cast<const float*>(e.aux) + (size_t)m * ldo + n0 : nullptr;
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
-    if (e.drop_keep != 0) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        uint64_t idx = (uint64_t)m * (uint64_t)N + (uint64_t)(n0 + j);
-        v[j] = dropout_keep(e.seed, e.drop_site, idx, e.drop_keep) ? v[j] * e.drop_scale : 0.f;
-      }
-    }
+    if (e.drop_keep != 0) dropout32(v, e, didx);
     if (full) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
-        float4 rr = r ? *reinterpret_cast<const float4*>(r + j) : make_float4(0, 0, 0, 0);
-        float4 w = make_float4(rr.x + e.alpha * v[j], rr.y + e.alpha * v[j + 1], rr.z + e.alpha * v[j + 2],
-                               rr.w + e.alpha * v[j + 3]);
-        *reinterpret_cast<float4*>(o + j) = w;
+        const float4 rr = r ? *reinterpret_cast<const float4*>(r + j) : make_float4(0, 0, 0, 0);
+        *reinterpret_cast<float4*>(o + j) = make_float4(fmaf(e.alpha, v[j], rr.x), fmaf(e.alpha, v[j + 1], rr.y),
+                                                        fmaf(e.alpha, v[j + 2], rr.z), fmaf(e.alpha, v[j + 3], rr.w));
       }
     } else {
       for (int j = 0; j < 32 && n0 + j < N; ++j) o[j] = (r ? r[j] : 0.f) + e.alpha * v[j];
@@ -156,21 +158,18 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
     bf16* ou = reinterpret_cast<bf16*>(e.out1) + (size_t)m * (ldo >> 1) + (n0 >> 1);
     bool valid = true;
     if (e.lengths) {
-      int b = m / e.rows_per_batch, t = m - b * e.rows_per_batch;
+      const int b = m / e.rows_per_batch, t = m - b * e.rows_per_batch;
       valid = t < e.lengths[b];
     }
     float u[16];
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
-      float a = bf16_round(v[j]), g = bf16_round(v[j + 1]);
-      v[j] = a; v[j + 1] = g;
-      u[j >> 1] = valid ? a * sigmoid_f(g) : 0.f;
+      v[j] = bf16_round(v[j]);
+      v[j + 1] = bf16_round(v[j + 1]);
+      u[j >> 1] = valid ? v[j] * sigmoid_f(v[j + 1]) : 0.f;
     }
     if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8)
-        *reinterpret_cast<uint4*>(og + j) = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
-                                                       pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+      store_bf16x32(og, v);
 #pragma unroll
       for (int j = 0; j < 16; j += 8)
         *reinterpret_cast<uint4*>(ou + j) = make_uint4(pack_bf16(u[j], u[j + 1]), pack_bf16(u[j + 2], u[j + 3]),
@@ -180,77 +179,65 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
       for (int j = 0; j < 16 && n0 + 2 * j < N; ++j) ou[j] = __float2bfloat16_rn(u[j]);
     }
   } else if (MODE == B2C_EPI_DSILU) {
-    // dz = bf16(acc * silu'(z[m,n]) [* dropout(site)])   z = aux (bf16)       (FFN backward)
+    // dz = bf16(dropout(bf16(acc)) * silu'(z[m,n]))   z = aux (bf16)       (FFN backward)
     bf16* o = reinterpret_cast<bf16*>(e.out0) + (size_t)m * ldo + n0;
     const bf16* z = reinterpret_cast<const bf16*>(e.aux) + (size_t)m * ldo + n0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (n0 + j < N) {
-        float g = bf16_round(v[j]);
-        if (e.drop_keep != 0) {
-          uint64_t idx = (uint64_t)m * (uint64_t)N + (uint64_t)(n0 + j);
-          g = dropout_keep(e.seed, e.drop_site, idx, e.drop_keep) ? g * e.drop_scale : 0.f;
-        }
-        v[j] = g * dsilu_f(__bfloat162float(z[j]));
-      }
-    }
+    float zz[32];
     if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8)
-        *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
-                                                      pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+      load_bf16x32(z, zz);
     } else {
-      for (int j = 0; j < 32 && n0 + j < N; ++j) o[j] = __float2bfloat16_rn(v[j]);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) zz[j] = (n0 + j < N) ? __bfloat162float(z[j]) : 0.f;
     }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
+    if (e.drop_keep != 0) dropout32(v, e, didx);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= dsilu_f(zz[j]);
+    if (full) store_bf16x32(o, v);
+    else for (int j = 0; j < 32 && n0 + j < N; ++j) o[j] = __float2bfloat16_rn(v[j]);
   } else if (MODE == B2C_EPI_RELU_MASK) {
     // out_bf16 = relu(acc+bias) * (t < len)    rows are (b, t) x rows_inner  (subsampling.py:725-753)
     bf16* o = reinterpret_cast<bf16*>(e.out0) + (size_t)m * ldo + n0;
     bool valid = true;
     if (e.lengths) {
-      int b = m / e.rows_per_batch, t = (m - b * e.rows_per_batch) / e.rows_inner;
+      const int b = m / e.rows_per_batch, t = (m - b * e.rows_per_batch) / e.rows_inner;
       valid = t < e.lengths[b];
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = valid ? fmaxf(bf16_round(v[j]), 0.f) : 0.f;
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 8)
-        *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
-                                                      pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
-    } else {
-      for (int j = 0; j < 32 && n0 + j < N; ++j) o[j] = __float2bfloat16_rn(v[j]);
-    }
+    for (int j = 0; j < 32; ++j) v[j] = valid ? fmaxf(v[j], 0.f) : 0.f;
+    if (full) store_bf16x32(o, v);
+    else for (int j = 0; j < 32 && n0 + j < N; ++j) o[j] = __float2bfloat16_rn(v[j]);
   } else if (MODE == B2C_EPI_RELU_BWD) {
     // out_bf16 = (aux_bf16[m,n] > 0) ? acc : 0     (gradient through ReLU + time mask: masked outputs are 0)
     bf16* o = reinterpret_cast<bf16*>(e.out0) + (size_t)m * ldo + n0;
     const bf16* y = reinterpret_cast<const bf16*>(e.aux) + (size_t)m * ldo + n0;
     if (full) {
+      float yy[32];
+      load_bf16x32(y, yy);
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        const uint4 yy = *reinterpret_cast<const uint4*>(y + j);
-        const uint32_t yw[4] = {yy.x, yy.y, yy.z, yy.w};
-        uint32_t ow[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 g = unpack_bf16(yw[q]);
-          ow[q] = pack_bf16(g.x > 0.f ? v[j + 2 * q] : 0.f, g.y > 0.f ? v[j + 2 * q + 1] : 0.f);
-        }
-        *reinterpret_cast<uint4*>(o + j) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-      }
+      for (int j = 0; j < 32; ++j) v[j] = yy[j] > 0.f ? v[j] : 0.f;
+      store_bf16x32(o, v);
     } else {
-      for (int j = 0; j < 32 && n0 + j < N; ++j)
-        o[j] = __float2bfloat16_rn(__bfloat162float(y[j]) > 0.f ? v[j] : 0.f);
+      for (int j = 0; j < 32 && n0 + j < N; ++j) o[j] = __float2bfloat16_rn(__bfloat162float(y[j]) > 0.f ? v[j] : 0.f);
     }
   } else if (MODE == B2C_EPI_ACCUM_F32) {
-    // out_f32[m,n] += alpha * acc  (weight gradients; atomic when split-K)
+    // out_f32[m,n] += alpha * acc  (weight gradients; vector reductions when split-K)
     float* o = reinterpret_cast<float*>(e.out0) + (size_t)m * ldo + n0;
+    const bool vec_ok = full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
     if (atomic) {
-      for (int j = 0; j < 32 && n0 + j < N; ++j) atomicAdd(o + j, e.alpha * v[j]);
-    } else if (full) {
+      if (vec_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) red_add_v4(o + j, e.alpha * v[j], e.alpha * v[j + 1], e.alpha * v[j + 2], e.alpha * v[j + 3]);
+      } else {
+        for (int j = 0; j < 32 && n0 + j < N; ++j) atomicAdd(o + j, e.alpha * v[j]);
+      }
+    } else if (vec_ok) {
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         float4 c = *reinterpret_cast<float4*>(o + j);
-        c.x += e.alpha * v[j]; c.y += e.alpha * v[j + 1]; c.z += e.alpha * v[j + 2]; c.w += e.alpha * v[j + 3];
+        c.x = fmaf(e.alpha, v[j], c.x); c.y = fmaf(e.alpha, v[j + 1], c.y);
+        c.z = fmaf(e.alpha, v[j + 2], c.z); c.w = fmaf(e.alpha, v[j + 3], c.w);
         *reinterpret_cast<float4*>(o + j) = c;
       }
     } else {
@@ -302,7 +289,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], kEpiWarps);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -391,7 +378,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int q = warp & 3;             // TMEM lane quarter this warp may access (= warp id % 4)
+    const int chalf = (warp - 4) >> 2;  // two warps share a quarter and split the 32-column chunks
     int as = 0, aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mn = tile / p.splits;
@@ -413,7 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         epi.out0 = reinterpret_cast<float*>(epi.out0) + (size_t)(tile % p.splits) * p.cv.C;  // tap-major columns
       }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chalf; c < BN / 32; c += 2) {
         uint32_t acc[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), acc);
         tmem_ld_wait();

@@ -147,7 +147,94 @@ dwconv3x3s2_fwd_kernel(const bf16* __restrict__ in, const float* __restrict__ w,
   }
 }
 
+// depthwise 3x3 s2 backward, data: dx[b,t1,f1,c] = (x[b,t1,f1,c] > 0) * sum_{kh,kw} dy[b,(t1+1-kh)/2,(f1+1-kw)/2,c] * w[c,kh,kw]
+// (dy rows t2 >= len_out count as zero: the forward masks the depthwise output before the pointwise conv)
+__global__ void __launch_bounds__(256)
+dwconv3x3s2_bwd_data_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ w,
+                            const int32_t* __restrict__ len_out, bf16* __restrict__ dx, int T1, int F1, int C, int T2,
+                            int F2) {
+  const int t1 = blockIdx.x, b = blockIdx.y;
+  const int lout = len_out ? len_out[b] : T2;
+  for (int cp = threadIdx.x; cp * 2 < C; cp += blockDim.x) {
+    const int c = cp * 2;
+    float w0[9], w1[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      w0[j] = bf16_round(w[(size_t)c * 9 + j]);
+      w1[j] = bf16_round(w[(size_t)(c + 1) * 9 + j]);
+    }
+    for (int f1 = 0; f1 < F1; ++f1) {
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int tn = t1 + 1 - kh;
+        if (tn < 0 || (tn & 1)) continue;
+        const int t2 = tn >> 1;
+        if (t2 >= T2 || t2 >= lout) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int fn = f1 + 1 - kw;
+          if (fn < 0 || (fn & 1)) continue;
+          const int f2 = fn >> 1;
+          if (f2 >= F2) continue;
+          const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(dy + (((size_t)b * T2 + t2) * F2 + f2) * C + c));
+          a0 = fmaf(w0[kh * 3 + kw], g.x, a0);
+          a1 = fmaf(w1[kh * 3 + kw], g.y, a1);
+        }
+      }
+      const size_t o = (((size_t)b * T1 + t1) * F1 + f1) * C + c;
+      const float2 xv = unpack_bf16(*reinterpret_cast<const uint32_t*>(x + o));
+      *reinterpret_cast<uint32_t*>(dx + o) = pack_bf16(xv.x > 0.f ? a0 : 0.f, xv.y > 0.f ? a1 : 0.f);
+    }
+  }
+}
+
+// weight / bias gradients of the depthwise 3x3 s2 conv: dw[c,kh,kw] += sum dy[b,t2,f2,c] * x[b,2t2+kh-1,2f2+kw-1,c]
+__global__ void __launch_bounds__(256)
+dwconv3x3s2_bwd_weight_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const int32_t* __restrict__ len_out,
+                              float* __restrict__ dw, float* __restrict__ dbias, int T1, int F1, int C, int T2, int F2,
+                              int rows_per_cta) {
+  const int b = blockIdx.y;
+  const int lout = len_out ? min(len_out[b], T2) : T2;
+  const int t2_0 = blockIdx.x * rows_per_cta, t2_1 = min(lout, t2_0 + rows_per_cta);
+  for (int cp = threadIdx.x; cp * 2 < C; cp += blockDim.x) {
+    const int c = cp * 2;
+    float g0[9], g1[9], d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) g0[j] = g1[j] = 0.f;
+    for (int t2 = t2_0; t2 < t2_1; ++t2) {
+      for (int f2 = 0; f2 < F2; ++f2) {
+        const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(dy + (((size_t)b * T2 + t2) * F2 + f2) * C + c));
+        d0 += g.x; d1 += g.y;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const int t = 2 * t2 - 1 + kh;
+          if (t < 0 || t >= T1) continue;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int f = 2 * f2 - 1 + kw;
+            if (f < 0 || f >= F1) continue;
+            const float2 xv = unpack_bf16(*reinterpret_cast<const uint32_t*>(x + (((size_t)b * T1 + t) * F1 + f) * C + c));
+            g0[kh * 3 + kw] = fmaf(g.x, xv.x, g0[kh * 3 + kw]);
+            g1[kh * 3 + kw] = fmaf(g.y, xv.y, g1[kh * 3 + kw]);
+          }
+        }
+      }
+    }
+    if (t2_1 > t2_0) {
+#pragma unroll
+      for (int j = 0; j < 9; ++j) {
+        atomicAdd(dw + (size_t)c * 9 + j, g0[j]);
+        atomicAdd(dw + (size_t)(c + 1) * 9 + j, g1[j]);
+      }
+      atomicAdd(dbias + c, d0);
+      atomicAdd(dbias + c + 1, d1);
+    }
+  }
+}
+
 }  // namespace b2c
+
 
 using namespace b2c;
 
@@ -179,6 +266,22 @@ extern "C" int b2c_dwconv3x3s2_fwd(const void* in_bf16, const float* w, const fl
   const int T2 = (T1 + 2 - 3) / 2 + 1, F2 = (F1 + 2 - 3) / 2 + 1;
   dwconv3x3s2_fwd_kernel<<<dim3(T2, B), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const bf16*>(in_bf16), w, bias, len_out, reinterpret_cast<bf16*>(out_bf16), T1, F1, C, T2, F2);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_dwconv3x3s2_bwd(const void* dy_bf16, const void* x_bf16, const float* w, const int32_t* len_out,
+                                   void* dx_bf16, float* dw, float* dbias, int B, int T1, int F1, int C, void* stream) {
+  B2C_REQUIRE(C % 2 == 0 && B > 0 && T1 > 0 && F1 > 0, "dwconv3x3s2_bwd: bad shape");
+  const int T2 = (T1 + 2 - 3) / 2 + 1, F2 = (F1 + 2 - 3) / 2 + 1;
+  dwconv3x3s2_bwd_data_kernel<<<dim3(T1, B), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(dy_bf16), reinterpret_cast<const bf16*>(x_bf16), w, len_out,
+      reinterpret_cast<bf16*>(dx_bf16), T1, F1, C, T2, F2);
+  B2C_LAUNCH_CHECK();
+  const int rows = 8;
+  dwconv3x3s2_bwd_weight_kernel<<<dim3((T2 + rows - 1) / rows, B), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const bf16*>(dy_bf16), reinterpret_cast<const bf16*>(x_bf16), len_out, dw, dbias, T1, F1, C, T2, F2,
+      rows);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
 }

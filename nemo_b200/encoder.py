@@ -608,7 +608,23 @@ class _EncoderFn(torch.autograd.Function):
             L.call("subsample_conv1_bwd", mt["mel"], dx1, mt["len_in32"], G["pre_encode.conv.0.weight"],
                    G["pre_encode.conv.0.bias"], B, Fs[0], Ts[0], C)
         else:
-            raise NotImplementedError("dw_striding backward is not built yet (forward / inference only)")
+            # dw_striding: x1 → [dw(ci) → pw(ci+1) + ReLU] x 2;  acts = [x1, dw2, pw3, dw5, pw6]
+            acts = ctx.S["sub"]
+            dyc = dylast  # gradient wrt the pre-activation of the last pointwise conv (already ReLU/mask gated)
+            for s_i, ci in reversed(list(enumerate((2, 5)))):
+                xin, dwo, pwo = acts[2 * s_i], acts[2 * s_i + 1], acts[2 * s_i + 2]
+                rows = B * Ts[s_i + 2] * Fs[s_i + 2]
+                gpw = G[f"pre_encode.conv.{ci + 1}.weight"].view(C, C)
+                _gemm(dyc, dwo, C, C, rows, L.EPI_ACCUM_F32, a_mn=1, b_mn=1, lda=C, ldb=C, out0=gpw, ldo=C)
+                L.call("colsum_bf16", dyc, G[f"pre_encode.conv.{ci + 1}.bias"], rows, C, C)
+                ddw = _empty(rows, C, dev=dev)
+                _gemm(dyc, W[f"pw{ci + 1}"], rows, C, C, L.EPI_BF16, b_mn=1, ldb=C, out0=ddw)
+                dxin = _empty(B, Ts[s_i + 1], Fs[s_i + 1], C, dev=dev)
+                L.call("dwconv3x3s2_bwd", ddw, xin, pe.conv[ci].weight.detach(), lens[s_i + 1], dxin,
+                       G[f"pre_encode.conv.{ci}.weight"], G[f"pre_encode.conv.{ci}.bias"], B, Ts[s_i + 1], Fs[s_i + 1], C)
+                dyc = dxin
+            L.call("subsample_conv1_bwd", mt["mel"], dyc, mt["len_in32"], G["pre_encode.conv.0.weight"],
+                   G["pre_encode.conv.0.bias"], B, Fs[0], Ts[0], C)
         if fg is not None:
             fg.ready(*fg.span("pre_encode."))
             return (None,) * (3 + len(plist))
