@@ -55,42 +55,56 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md) through NVML in a background thread
+    (the `nvidia-smi -lms` subprocess of the recipe measurably stalls kernel launches on this box; same counters)."""
 
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index=0, period=0.2):
+        self.index, self.period, self.rows, self._stop, self.thr, self.err = index, period, [], False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+
+            def loop():
+                while not self._stop:
+                    try:
+                        mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        try:
+                            rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.rows.append((mhz, rs))
+                    except Exception as e:  # noqa: BLE001
+                        self.err = repr(e)
+                    time.sleep(self.period)
+
+            self.thr = threading.Thread(target=loop, daemon=True)
+            self.thr.start()
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = float(r[1])
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        self._stop = True
+        if self.thr is not None:
+            self.thr.join(timeout=2)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = set()
+        for _, rs in self.rows:
+            for bit, name in self.REASONS.items():
+                if rs & bit:
+                    reasons.add(name)
+        return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(self.max_mhz), "reasons": sorted(reasons),
+                "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------------ reference / CPU arm
@@ -104,19 +118,30 @@ def cpu_reference_step(O, sd, wav, wlen, cfg):
     (y.float().pow(2).mean()).backward()
 
 
-def cpu_baseline(steps=2, warmup=1, batch=1):
+def host_threads():
+    """Threads the CPU arm uses: the cores this process may run on, capped at 32 — PyTorch-eager on this path stops
+    scaling well before that (128 threads measured 40x SLOWER than 8 on the pool's hosts: 0.13 vs 4.8 audio-s/s)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 32))
+
+
+def cpu_baseline(steps=2, warmup=1, batch=1, secs=10.0):
     from oracle import conformer_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_threads())
     sd = O.init_state_dict(seed=0, **LARGE)
-    wav, wlen = O.synthetic_waveforms(batch, SECS)
+    wav, wlen = O.synthetic_waveforms(batch, secs)
     for _ in range(warmup):
         cpu_reference_step(O, sd, wav, wlen, LARGE)
     t0 = time.perf_counter()
     for _ in range(steps):
         cpu_reference_step(O, sd, wav, wlen, LARGE)
     dt = (time.perf_counter() - t0) / steps
-    return {"value": batch * SECS / dt, "unit": "audio-sec/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} steps of {batch}x{int(SECS)} s fwd+bwd (fp32 oracle port of the reference modules, PyTorch eager)",
+    return {"value": batch * secs / dt, "unit": "audio-sec/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} steps of {batch}x{int(secs)} s mel+fwd+bwd, Conformer-CTC-Large (fp32 oracle port of the reference "
+                      f"modules, PyTorch eager, {torch.get_num_threads()} threads)",
             "ms_per_step": dt * 1e3}
 
 
@@ -130,7 +155,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "Conformer-CTC-Large 18L d512 h8 k31 striding4x fwd+bwd, 30 s utterances",
-                   "sample": "1x30 s per step on host CPU cores"},
+                   "sample": "1x10 s utterance per step on host CPU cores"},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "audio-sec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
