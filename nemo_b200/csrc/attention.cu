@@ -66,6 +66,28 @@ __device__ __forceinline__ void load_tile(bf16* s, const bf16* g, long long row0
   }
 }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 → the 16 destination bytes are zero-filled, nothing is read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem)), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// asynchronous variant of load_tile (LDGSTS: global → smem without staging registers); rows outside [0, limit) → 0
+template <int DK>
+__device__ __forceinline__ void load_tile_async(bf16* s, const bf16* g, long long row0, int nrows, long long limit, int ld,
+                                                int tid, int nthreads) {
+  constexpr int P = DK + 8;
+  constexpr int VPR = DK / 8;
+  for (int i = tid; i < nrows * VPR; i += nthreads) {
+    const int r = i / VPR, v = i - r * VPR;
+    const long long gr = row0 + r;
+    const bool ok = gr >= 0 && gr < limit;
+    cp_async16(s + r * P + v * 8, ok ? g + gr * ld + v * 8 : g, ok);
+  }
+}
+
 // A fragments (16 rows x DK) of bf16(q + bias) for this warp, straight from global.  rows >= T → 0
 template <int DK>
 __device__ __forceinline__ void load_q_frags(uint32_t (&fr)[DK / 16][4], const bf16* q, int ld, int row0, int T,
@@ -166,10 +188,9 @@ __global__ void __launch_bounds__(128)
 relpos_attn_fwd_kernel(const AttnArgs a, bf16* __restrict__ ctx, float* __restrict__ lse_out) {
   constexpr int P = DK + 8;
   extern __shared__ __align__(16) uint8_t smraw[];
-  bf16* sK = reinterpret_cast<bf16*>(smraw);
-  bf16* sV = sK + BKV * P;
-  bf16* sP = sV + BKV * P;                               // 128 band rows
-  float* scr_all = reinterpret_cast<float*>(sP + 128 * P);  // 4 x 16 x SCR_PITCH
+  constexpr int STAGE = (BKV + BKV + 128) * P;  // K, V, 128 band rows of P
+  bf16* stage0 = reinterpret_cast<bf16*>(smraw);
+  float* scr_all = reinterpret_cast<float*>(stage0 + 2 * STAGE);  // 4 x 16 x SCR_PITCH
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
   const int i0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const int T = a.T, ld = 3 * a.d;
@@ -192,13 +213,22 @@ relpos_attn_fwd_kernel(const AttnArgs a, bf16* __restrict__ ctx, float* __restri
   const float sc2 = a.scale * kLog2e;
 
   const int n_kv = (len + BKV - 1) / BKV;  // keys >= len contribute exactly 0 (exp(-1e4 - m) == 0 in fp32)
+  auto issue = [&](int jt) {  // 2-stage cp.async ring: tile jt+1 streams in while tile jt is on the tensor cores
+    bf16* st = stage0 + (jt & 1) * STAGE;
+    const int j0 = jt * BKV;
+    load_tile_async<DK>(st, kb, j0, BKV, T, ld, tid, 128);
+    load_tile_async<DK>(st + BKV * P, vb, j0, BKV, T, ld, tid, 128);
+    load_tile_async<DK>(st + 2 * BKV * P, pb, (long long)T - 1 - (i0 + 63) + j0, 128, 2LL * T - 1, a.d, tid, 128);
+    cp_async_commit();
+  };
+  if (n_kv > 0) issue(0);
   for (int jt = 0; jt < n_kv; ++jt) {
     const int j0 = jt * BKV;
+    if (jt + 1 < n_kv) { issue(jt + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
-    load_tile<DK>(sK, kb, j0, BKV, T, ld, tid, 128);
-    load_tile<DK>(sV, vb, j0, BKV, T, ld, tid, 128);
-    load_tile<DK>(sP, pb, (long long)T - 1 - (i0 + 63) + j0, 128, 2LL * T - 1, a.d, tid, 128);
-    __syncthreads();
+    const bf16* sK = stage0 + (jt & 1) * STAGE;
+    const bf16* sV = sK + BKV * P;
+    const bf16* sP = sV + BKV * P;
     float s[8][4];
     score_tile<DK>(s, qu, qv, sK, sP, scr, warp, lane);
     // mask + online softmax (exp2 domain)
@@ -255,6 +285,7 @@ relpos_attn_fwd_kernel(const AttnArgs a, bf16* __restrict__ ctx, float* __restri
       o[nt][2] *= corr[1]; o[nt][3] *= corr[1];
     }
     mma_pv<DK, 4>(o, pa, sV, lane);
+    __syncthreads();  // every warp is done with this stage before the next issue() overwrites it
   }
   // finalise: rows >= len (fully masked queries) output exactly 0 (second masked_fill, :137-138)
 #pragma unroll
@@ -281,10 +312,9 @@ relpos_attn_bwd_q_kernel(const AttnArgs a, const bf16* __restrict__ ctx, const b
                          float* __restrict__ dbias_v, bf16* __restrict__ ws_ds, bf16* __restrict__ ws_p, int Tp) {
   constexpr int P = DK + 8;
   extern __shared__ __align__(16) uint8_t smraw[];
-  bf16* sK = reinterpret_cast<bf16*>(smraw);
-  bf16* sV = sK + BKV * P;
-  bf16* sP = sV + BKV * P;
-  float* scr_all = reinterpret_cast<float*>(sP + 128 * P);
+  constexpr int STAGE = (BKV + BKV + 128) * P;
+  bf16* stage0 = reinterpret_cast<bf16*>(smraw);
+  float* scr_all = reinterpret_cast<float*>(stage0 + 2 * STAGE);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
   const int i0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const int T = a.T, ld = 3 * a.d;
@@ -335,6 +365,15 @@ relpos_attn_bwd_q_kernel(const AttnArgs a, const bf16* __restrict__ ctx, const b
   bf16* wp = ws_p + ((size_t)(b * a.H + h) * T) * Tp;
   const int n_kv_all = (T + BKV - 1) / BKV;
   const int n_kv = (len + BKV - 1) / BKV;
+  auto issue = [&](int jt) {
+    bf16* st = stage0 + (jt & 1) * STAGE;
+    const int j0 = jt * BKV;
+    load_tile_async<DK>(st, kb, j0, BKV, T, ld, tid, 128);
+    load_tile_async<DK>(st + BKV * P, vb, j0, BKV, T, ld, tid, 128);
+    load_tile_async<DK>(st + 2 * BKV * P, pb, (long long)T - 1 - (i0 + 63) + j0, 128, 2LL * T - 1, a.d, tid, 128);
+    cp_async_commit();
+  };
+  if (n_kv > 0) issue(0);
   for (int jt = 0; jt < n_kv_all; ++jt) {
     const int j0 = jt * BKV;
     if (jt >= n_kv) {  // tiles fully beyond the valid length: dS = P = 0, just clear the workspaces
@@ -350,11 +389,11 @@ relpos_attn_bwd_q_kernel(const AttnArgs a, const bf16* __restrict__ ctx, const b
         }
       continue;
     }
+    if (jt + 1 < n_kv) { issue(jt + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
-    load_tile<DK>(sK, kb, j0, BKV, T, ld, tid, 128);
-    load_tile<DK>(sV, vb, j0, BKV, T, ld, tid, 128);
-    load_tile<DK>(sP, pb, (long long)T - 1 - (i0 + 63) + j0, 128, 2LL * T - 1, a.d, tid, 128);
-    __syncthreads();
+    const bf16* sK = stage0 + (jt & 1) * STAGE;
+    const bf16* sV = sK + BKV * P;
+    const bf16* sP = sV + BKV * P;
     float s[8][4];
     score_tile<DK>(s, qu, qv, sK, sP, scr, warp, lane);
     float dp[8][4];
@@ -420,6 +459,7 @@ relpos_attn_bwd_q_kernel(const AttnArgs a, const bf16* __restrict__ ctx, const b
       }
     }
     mma_pv<DK, BAND / 16>(dqv, ua, sP + (3 - warp) * 16 * P, lane);
+    __syncthreads();
   }
   // dq = dQ_u + dQ_v → bf16 into the q slot of dqkv
 #pragma unroll
@@ -482,50 +522,61 @@ relpos_attn_bwd_kv_kernel(const AttnArgs a, const bf16* __restrict__ dctx, const
     dk_[nt][0] = dk_[nt][1] = dk_[nt][2] = dk_[nt][3] = 0.f;
     dv_[nt][0] = dv_[nt][1] = dv_[nt][2] = dv_[nt][3] = 0.f;
   }
+  constexpr int STAGE = 2 * 64 * P + 2 * 64 * PX;
   const int n_q = (len + 63) / 64;  // query rows >= len have dS = P = 0
-  for (int it = 0; it < n_q; ++it) {
+  auto issue = [&](int it) {       // 2-stage cp.async ring over the query tiles
+    bf16* st = sQ + (it & 1) * STAGE;
     const int i0 = it * 64;
-    __syncthreads();
-    // q + u (bf16) tile
-    for (int idx = tid; idx < 64 * (DK / 2); idx += 128) {
-      const int r = idx / (DK / 2), cp = idx - r * (DK / 2);
-      uint32_t val = 0u;
-      if (i0 + r < T) {
-        float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(qb + (size_t)(i0 + r) * ld + cp * 2));
-        val = pack_bf16(v.x + bu[cp * 2], v.y + bu[cp * 2 + 1]);
-      }
-      *reinterpret_cast<uint32_t*>(sQ + r * P + cp * 2) = val;
-    }
-    load_tile<DK>(sO, dob, i0, 64, T, a.d, tid, 128);
+    load_tile_async<DK>(st, qb, i0, 64, T, ld, tid, 128);                // raw q (bias added in place below)
+    load_tile_async<DK>(st + 64 * P, dob, i0, 64, T, a.d, tid, 128);     // dO
+    bf16* d1 = st + 2 * 64 * P;
+    bf16* d2 = d1 + 64 * PX;
     for (int idx = tid; idx < 64 * 8; idx += 128) {
       const int r = idx >> 3, v = idx & 7;
-      uint4 x = make_uint4(0, 0, 0, 0), y = make_uint4(0, 0, 0, 0);
-      if (i0 + r < T && j0 + v * 8 < Tp) {
-        x = *reinterpret_cast<const uint4*>(wds + (size_t)(i0 + r) * Tp + j0 + v * 8);
-        y = *reinterpret_cast<const uint4*>(wp + (size_t)(i0 + r) * Tp + j0 + v * 8);
+      const bool ok = (i0 + r < T) && (j0 + v * 8 < Tp);
+      const size_t off = ok ? (size_t)(i0 + r) * Tp + j0 + v * 8 : 0;
+      cp_async16(d1 + r * PX + v * 8, wds + off, ok);
+      cp_async16(d2 + r * PX + v * 8, wp + off, ok);
+    }
+    cp_async_commit();
+  };
+  if (n_q > 0) issue(0);
+  for (int it = 0; it < n_q; ++it) {
+    if (it + 1 < n_q) { issue(it + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncthreads();
+    bf16* tQ = sQ + (it & 1) * STAGE;
+    const bf16* tO = tQ + 64 * P;
+    const bf16* tDS = tO + 64 * P;
+    const bf16* tPd = tDS + 64 * PX;
+    // q → bf16(q + u) in place (each thread owns its elements; rows >= T are zero-filled and must stay zero)
+    for (int idx = tid; idx < 64 * (DK / 2); idx += 128) {
+      const int r = idx / (DK / 2), cp = idx - r * (DK / 2);
+      if (it * 64 + r < T) {
+        uint32_t* pq = reinterpret_cast<uint32_t*>(tQ + r * P + cp * 2);
+        const float2 v = unpack_bf16(*pq);
+        *pq = pack_bf16(v.x + bu[cp * 2], v.y + bu[cp * 2 + 1]);
       }
-      *reinterpret_cast<uint4*>(sDS + r * PX + v * 8) = x;
-      *reinterpret_cast<uint4*>(sPd + r * PX + v * 8) = y;
     }
     __syncthreads();
-    // this warp's 16 keys: columns warp*16.. of sDS / sPd (A = X^T via ldmatrix.trans)
+    // this warp's 16 keys: columns warp*16.. of dS / Pd (A = X^T via ldmatrix.trans)
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       uint32_t ads[4], apd[4];
       const int mi = lane >> 3;
       const int krow = ks * 16 + (mi >> 1) * 8 + (lane & 7);
       const int mcol = warp * 16 + (mi & 1) * 8;
-      ldsm_x4_trans(ads, sDS + krow * PX + mcol);
-      ldsm_x4_trans(apd, sPd + krow * PX + mcol);
+      ldsm_x4_trans(ads, tDS + krow * PX + mcol);
+      ldsm_x4_trans(apd, tPd + krow * PX + mcol);
 #pragma unroll
       for (int nt = 0; nt < DK / 8; ++nt) {
         uint32_t b0, b1;
-        ldsm_x2_trans(b0, b1, sQ + (ks * 16 + (lane & 15)) * P + nt * 8);
+        ldsm_x2_trans(b0, b1, tQ + (ks * 16 + (lane & 15)) * P + nt * 8);
         mma16816(dk_[nt], ads, b0, b1);
-        ldsm_x2_trans(b0, b1, sO + (ks * 16 + (lane & 15)) * P + nt * 8);
+        ldsm_x2_trans(b0, b1, tO + (ks * 16 + (lane & 15)) * P + nt * 8);
         mma16816(dv_[nt], apd, b0, b1);
       }
     }
+    __syncthreads();
   }
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr) {
@@ -633,7 +684,7 @@ static int fill_args(AttnArgs& a, const void* qkv, const void* pos, const float*
 }
 
 template <int DK>
-static size_t smem_q() { return (size_t)(64 + 64 + 128) * (DK + 8) * 2 + 4 * 16 * SCR_PITCH * 4; }
+static size_t smem_q() { return (size_t)2 * (64 + 64 + 128) * (DK + 8) * 2 + 4 * 16 * SCR_PITCH * 4; }
 
 template <int DK>
 static int launch_fwd(const AttnArgs& a, bf16* ctx, float* lse, cudaStream_t st) {
@@ -652,7 +703,7 @@ template <int DK>
 static int launch_bwd(const AttnArgs& a, const bf16* ctx, const bf16* dctx, const float* lse, bf16* dqkv, float* dpos,
                       float* dbu, float* dbv, bf16* ws_ds, bf16* ws_p, int Tp, cudaStream_t st) {
   const size_t smem1 = smem_q<DK>();
-  const size_t smem2 = (size_t)2 * 64 * (DK + 8) * 2 + (size_t)2 * 64 * (BKV + 8) * 2;
+  const size_t smem2 = 2 * ((size_t)2 * 64 * (DK + 8) * 2 + (size_t)2 * 64 * (BKV + 8) * 2);
   const size_t smem3 = (size_t)64 * (DK + 8) * 2 + (size_t)64 * 72 * 2;
   static bool set = false;
   if (!set) {
