@@ -99,7 +99,7 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
         v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
       }
     } else {
-      for (int j = 0; j < 32 && n0 + j < N; ++j) v[j] += e.bias[n0 + j];
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) v[j] += e.bias[n0 + j];
     }
   }
   const size_t ldo = (size_t)e.ldo;
@@ -109,7 +109,7 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
     // out_bf16[m, n] = bf16(acc + bias)
     bf16* o = reinterpret_cast<bf16*>(e.out0) + (size_t)m * ldo + n0;
     if (full) store_bf16x32(o, v);
-    else for (int j = 0; j < 32 && n0 + j < N; ++j) o[j] = __float2bfloat16_rn(v[j]);
+    else _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) o[j] = __float2bfloat16_rn(v[j]);
   } else if (MODE == B2C_EPI_SILU) {
     // z = bf16(acc+bias) → out0 ; h = bf16(dropout(silu(z))) → out1   (conformer_modules.py:383-385)
     bf16* oz = reinterpret_cast<bf16*>(e.out0) + (size_t)m * ldo + n0;
@@ -129,7 +129,7 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
       store_bf16x32(oz, v);
       store_bf16x32(oh, h);
     } else {
-      for (int j = 0; j < 32 && n0 + j < N; ++j) {
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) {
         oz[j] = __float2bfloat16_rn(v[j]);
         oh[j] = __float2bfloat16_rn(h[j]);
       }
@@ -149,7 +149,7 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
                                                         fmaf(e.alpha, v[j + 2], rr.z), fmaf(e.alpha, v[j + 3], rr.w));
       }
     } else {
-      for (int j = 0; j < 32 && n0 + j < N; ++j) o[j] = (r ? r[j] : 0.f) + e.alpha * v[j];
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) o[j] = (r ? r[j] : 0.f) + e.alpha * v[j];
     }
   } else if (MODE == B2C_EPI_GLU_MASK) {
     // columns interleaved (value, gate). g = bf16(acc+bias) → out0 [M, N];
@@ -175,8 +175,8 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
         *reinterpret_cast<uint4*>(ou + j) = make_uint4(pack_bf16(u[j], u[j + 1]), pack_bf16(u[j + 2], u[j + 3]),
                                                        pack_bf16(u[j + 4], u[j + 5]), pack_bf16(u[j + 6], u[j + 7]));
     } else {
-      for (int j = 0; j < 32 && n0 + j < N; ++j) og[j] = __float2bfloat16_rn(v[j]);
-      for (int j = 0; j < 16 && n0 + 2 * j < N; ++j) ou[j] = __float2bfloat16_rn(u[j]);
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) og[j] = __float2bfloat16_rn(v[j]);
+      _Pragma("unroll") for (int j = 0; j < 16; ++j) if (n0 + 2 * j < N) ou[j] = __float2bfloat16_rn(u[j]);
     }
   } else if (MODE == B2C_EPI_DSILU) {
     // dz = bf16(dropout(bf16(acc)) * silu'(z[m,n]))   z = aux (bf16)       (FFN backward)
@@ -195,7 +195,7 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= dsilu_f(zz[j]);
     if (full) store_bf16x32(o, v);
-    else for (int j = 0; j < 32 && n0 + j < N; ++j) o[j] = __float2bfloat16_rn(v[j]);
+    else _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) o[j] = __float2bfloat16_rn(v[j]);
   } else if (MODE == B2C_EPI_RELU_MASK) {
     // out_bf16 = relu(acc+bias) * (t < len)    rows are (b, t) x rows_inner  (subsampling.py:725-753)
     bf16* o = reinterpret_cast<bf16*>(e.out0) + (size_t)m * ldo + n0;
@@ -207,7 +207,7 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = valid ? fmaxf(v[j], 0.f) : 0.f;
     if (full) store_bf16x32(o, v);
-    else for (int j = 0; j < 32 && n0 + j < N; ++j) o[j] = __float2bfloat16_rn(v[j]);
+    else _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) o[j] = __float2bfloat16_rn(v[j]);
   } else if (MODE == B2C_EPI_RELU_BWD) {
     // out_bf16 = (aux_bf16[m,n] > 0) ? acc : 0     (gradient through ReLU + time mask: masked outputs are 0)
     bf16* o = reinterpret_cast<bf16*>(e.out0) + (size_t)m * ldo + n0;
@@ -219,7 +219,7 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
       for (int j = 0; j < 32; ++j) v[j] = yy[j] > 0.f ? v[j] : 0.f;
       store_bf16x32(o, v);
     } else {
-      for (int j = 0; j < 32 && n0 + j < N; ++j) o[j] = __float2bfloat16_rn(__bfloat162float(y[j]) > 0.f ? v[j] : 0.f);
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) o[j] = __float2bfloat16_rn(__bfloat162float(y[j]) > 0.f ? v[j] : 0.f);
     }
   } else if (MODE == B2C_EPI_ACCUM_F32) {
     // out_f32[m,n] += alpha * acc  (weight gradients; vector reductions when split-K)
@@ -230,7 +230,7 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
 #pragma unroll
         for (int j = 0; j < 32; j += 4) red_add_v4(o + j, e.alpha * v[j], e.alpha * v[j + 1], e.alpha * v[j + 2], e.alpha * v[j + 3]);
       } else {
-        for (int j = 0; j < 32 && n0 + j < N; ++j) atomicAdd(o + j, e.alpha * v[j]);
+        _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) atomicAdd(o + j, e.alpha * v[j]);
       }
     } else if (vec_ok) {
 #pragma unroll
@@ -241,7 +241,7 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
         *reinterpret_cast<float4*>(o + j) = c;
       }
     } else {
-      for (int j = 0; j < 32 && n0 + j < N; ++j) o[j] += e.alpha * v[j];
+      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) o[j] += e.alpha * v[j];
     }
   }
 }

@@ -314,7 +314,7 @@ def attn_reference(q, k, v, p, bu, bv, lengths):
     return (attn @ vv).transpose(1, 2).reshape(B, T, h * dk)
 
 
-@pytest.mark.parametrize("B,T,h,dk", [(2, 64, 2, 64), (3, 131, 4, 64), (2, 200, 2, 128), (2, 751, 2, 64)])
+@pytest.mark.parametrize("B,T,h,dk", [(3, 26, 4, 64), (2, 64, 2, 64), (3, 131, 4, 64), (2, 200, 2, 128), (2, 751, 2, 64)])
 def test_relpos_attention_fwd_bwd(B, T, h, dk):
     d = h * dk
     lengths = torch.tensor([T, (2 * T) // 3, 5][:B], dtype=torch.int32, device=DEV)
