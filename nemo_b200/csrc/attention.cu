@@ -29,6 +29,11 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(smem_u32(p)));
 }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
 __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -113,19 +118,22 @@ __device__ __forceinline__ void load_q_frags(uint32_t (&fr)[DK / 16][4], const b
   }
 }
 
-// S(16 x 64) (+)= A(16 x DK) * Bt where Bt rows (keys / band rows) live in smem [row][DK+8]
+// S(16 x 8*NT) (+)= A(16 x DK) * Bt where Bt rows (keys / band rows) live in smem [row][DK+8].
+// One ldmatrix.x4 fetches the B fragments of two adjacent 8-column tiles for one 16-wide k step.
 template <int DK, int NT>
 __device__ __forceinline__ void mma_qk(float (&acc)[NT][4], const uint32_t (&a)[DK / 16][4], const bf16* sB, int lane) {
   constexpr int P = DK + 8;
-  const int g = lane >> 2, c = lane & 3;
+  static_assert(NT % 2 == 0, "NT must be even");
+  const int mrow = ((lane >> 4) << 3) + (lane & 7);  // matrices 2,3 → second n-tile
+  const int mcol = ((lane >> 3) & 1) << 3;           // matrices 1,3 → k offset 8
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
+  for (int nt = 0; nt < NT; nt += 2) {
 #pragma unroll
     for (int ks = 0; ks < DK / 16; ++ks) {
-      const bf16* p = sB + (nt * 8 + g) * P + ks * 16 + 2 * c;
-      const uint32_t b0 = *reinterpret_cast<const uint32_t*>(p);
-      const uint32_t b1 = *reinterpret_cast<const uint32_t*>(p + 8);
-      mma16816(acc[nt], a[ks], b0, b1);
+      uint32_t b[4];
+      ldsm_x4(b, sB + (nt * 8 + mrow) * P + ks * 16 + mcol);
+      mma16816(acc[nt], a[ks], b[0], b[1]);
+      mma16816(acc[nt + 1], a[ks], b[2], b[3]);
     }
   }
 }
@@ -176,6 +184,14 @@ __device__ __forceinline__ void score_tile(float (&s)[8][4], const uint32_t (&qu
   }
 }
 
+// keep decisions for the element pair (i, j), (i, j+1) with j even: bit0 / bit1
+__device__ __forceinline__ uint32_t attn_keep2(const AttnArgs& a, uint64_t row_base, int j) {
+  const uint32_t hsh = dropout_hash(a.seed, a.site, (row_base + (uint64_t)j) >> 1);
+  return ((hsh & 0xFFFFu) < a.drop_keep ? 1u : 0u) | ((hsh >> 16) < a.drop_keep ? 2u : 0u);
+}
+__device__ __forceinline__ uint64_t attn_row_base(const AttnArgs& a, int b, int h, int i) {
+  return ((uint64_t)((b * a.H + h) * (int64_t)a.T + i)) * (uint64_t)((a.T + 1) & ~1);
+}
 __device__ __forceinline__ bool attn_keep(const AttnArgs& a, int b, int h, int i, int j) {
   // row pitch rounded up to even so the (j, j+1) pairs a thread owns share one hash
   const uint64_t idx = ((uint64_t)((b * a.H + h) * (int64_t)a.T + i)) * (uint64_t)((a.T + 1) & ~1) + (uint64_t)j;
@@ -211,6 +227,7 @@ relpos_attn_fwd_kernel(const AttnArgs a, bf16* __restrict__ ctx, float* __restri
   float m[2] = {-1e30f, -1e30f}, l[2] = {0.f, 0.f};
   const int row_g[2] = {i0 + warp * 16 + g, i0 + warp * 16 + g + 8};
   const float sc2 = a.scale * kLog2e;
+  const uint64_t rbase[2] = {attn_row_base(a, b, h, row_g[0]), attn_row_base(a, b, h, row_g[1])};
 
   const int n_kv = (len + BKV - 1) / BKV;  // keys >= len contribute exactly 0 (exp(-1e4 - m) == 0 in fp32)
   auto issue = [&](int jt) {  // 2-stage cp.async ring: tile jt+1 streams in while tile jt is on the tensor cores
@@ -233,15 +250,15 @@ relpos_attn_fwd_kernel(const AttnArgs a, bf16* __restrict__ ctx, float* __restri
     score_tile<DK>(s, qu, qv, sK, sP, scr, warp, lane);
     // mask + online softmax (exp2 domain)
     float mx[2] = {-1e30f, -1e30f};
+    const bool rvalid[2] = {row_g[0] < len, row_g[1] < len};
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
+      const int jb = j0 + nt * 8 + 2 * c;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int j = j0 + nt * 8 + 2 * c + (e & 1);
-        const int rr = e >> 1;
-        const bool valid = (j < len) && (row_g[rr] < len);
+        const bool valid = (jb + (e & 1) < len) & rvalid[e >> 1];
         s[nt][e] = valid ? s[nt][e] * sc2 : -1e30f;
-        mx[rr] = fmaxf(mx[rr], s[nt][e]);
+        mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
       }
     }
 #pragma unroll
@@ -262,13 +279,17 @@ relpos_attn_fwd_kernel(const AttnArgs a, bf16* __restrict__ ctx, float* __restri
       float p[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int rr = e >> 1;
-        p[e] = (s[nt][e] > -1e29f) ? exp2f(s[nt][e] - m[rr]) : 0.f;
-        rs[rr] += p[e];
-        if (a.drop_keep != 0) {
-          const int j = j0 + nt * 8 + 2 * c + (e & 1);
-          p[e] = attn_keep(a, b, h, row_g[rr], j) ? p[e] * a.drop_scale : 0.f;
-        }
+        p[e] = exp2f(s[nt][e] - m[e >> 1]);     // masked entries: exp2(-1e30 - m) == 0 (m is finite for valid rows)
+        p[e] = (s[nt][e] > -1e29f) ? p[e] : 0.f;  // fully-masked rows (m == -1e30)
+        rs[e >> 1] += p[e];
+      }
+      if (a.drop_keep != 0) {
+        const int jb = j0 + nt * 8 + 2 * c;
+        const uint32_t k0 = attn_keep2(a, rbase[0], jb), k1 = attn_keep2(a, rbase[1], jb);
+        p[0] = (k0 & 1u) ? p[0] * a.drop_scale : 0.f;
+        p[1] = (k0 & 2u) ? p[1] * a.drop_scale : 0.f;
+        p[2] = (k1 & 1u) ? p[2] * a.drop_scale : 0.f;
+        p[3] = (k1 & 2u) ? p[3] * a.drop_scale : 0.f;
       }
       pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p[0], p[1]);
       pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p[2], p[3]);
@@ -361,6 +382,8 @@ relpos_attn_bwd_q_kernel(const AttnArgs a, const bf16* __restrict__ ctx, const b
     dqv[nt][0] = dqv[nt][1] = dqv[nt][2] = dqv[nt][3] = 0.f;
   }
   const float sc2 = a.scale * kLog2e;
+  const uint64_t rbase[2] = {attn_row_base(a, b, h, row_g[0]), attn_row_base(a, b, h, row_g[1])};
+  const bool rvalid[2] = {row_g[0] < len, row_g[1] < len};
   bf16* wds = ws_ds + ((size_t)(b * a.H + h) * T) * Tp;
   bf16* wp = ws_p + ((size_t)(b * a.H + h) * T) * Tp;
   const int n_kv_all = (T + BKV - 1) / BKV;
@@ -405,19 +428,20 @@ relpos_attn_bwd_q_kernel(const AttnArgs a, const bf16* __restrict__ ctx, const b
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       float ds[4], pd[4];
+      const int jb = j0 + nt * 8 + 2 * c;
+      uint32_t keep[2] = {3u, 3u};
+      if (a.drop_keep != 0) {
+        keep[0] = attn_keep2(a, rbase[0], jb);
+        keep[1] = attn_keep2(a, rbase[1], jb);
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int rr = e >> 1;
-        const int j = j0 + nt * 8 + 2 * c + (e & 1);
-        const bool valid = (j < len) && (row_g[rr] < len);
-        float p = valid ? exp2f(s[nt][e] * sc2 - lse2[rr]) : 0.f;
-        float dpe = dp[nt][e];
-        pd[e] = p;
-        if (a.drop_keep != 0) {
-          const bool keep = valid && attn_keep(a, b, h, row_g[rr], j);
-          pd[e] = keep ? p * a.drop_scale : 0.f;
-          dpe = keep ? dpe * a.drop_scale : 0.f;
-        }
+        const bool valid = (jb + (e & 1) < len) & rvalid[rr];
+        const float p = valid ? exp2f(s[nt][e] * sc2 - lse2[rr]) : 0.f;
+        const bool kp = (keep[rr] >> (e & 1)) & 1u;
+        pd[e] = kp ? p * a.drop_scale : 0.f;
+        const float dpe = kp ? dp[nt][e] * a.drop_scale : 0.f;
         ds[e] = p * (dpe - delta[rr]) * a.scale;
       }
       dsa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(ds[0], ds[1]);
@@ -631,12 +655,37 @@ relpos_attn_bwd_pos_kernel(const AttnArgs a, const bf16* __restrict__ ws_ds, flo
         }
         *reinterpret_cast<uint32_t*>(sQ + r * P + cp * 2) = val;
       }
-      for (int idx = tid; idx < 64 * 64; idx += 128) {
-        const int il = idx >> 6, rl = idx & 63;
-        const int i = i0 + il, j = i - (T - 1) + r0 + rl;
-        bf16 v = __float2bfloat16_rn(0.f);
-        if (i < T && j >= 0 && j < T && r0 + rl < R) v = wds[(size_t)i * Tp + j];
-        sX[il * PX + rl] = v;
+      {
+        // diagonal gather: row il of the tile holds dS[i, j] for j = i-(T-1)+r0 .. +63; each thread moves 32 of them
+        const int il = tid >> 1, half = tid & 1;
+        const int i = i0 + il;
+        const int js = i - (T - 1) + r0 + half * 32;
+        uint32_t* dst = reinterpret_cast<uint32_t*>(sX + il * PX + half * 32);
+        if (i > hi) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) dst[k] = 0u;
+        } else if (js >= 0 && js + 32 <= Tp) {  // columns [T, Tp) of the staged dS are zeros
+          const bf16* src = wds + (size_t)i * Tp + js;
+          if ((js & 1) == 0) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) dst[k] = reinterpret_cast<const uint32_t*>(src)[k];
+          } else {
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(src - 1);
+            uint32_t prev = w[0];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const uint32_t nxt = (k < 15 || js + 32 < Tp) ? w[k + 1] : 0u;
+              dst[k] = __funnelshift_r(prev, nxt, 16);
+              prev = nxt;
+            }
+          }
+        } else {
+          bf16* d16 = reinterpret_cast<bf16*>(dst);
+          for (int k = 0; k < 32; ++k) {
+            const int j = js + k;
+            d16[k] = (j >= 0 && j < T) ? wds[(size_t)i * Tp + j] : __float2bfloat16_rn(0.f);
+          }
+        }
       }
       __syncthreads();
 #pragma unroll

@@ -104,6 +104,36 @@ def _empty(*shape, dtype=BF16, dev=None):
     return torch.empty(*shape, dtype=dtype, device=dev)
 
 
+class _Arena:
+    """Bump allocator over fixed-size chunks obtained from torch's caching allocator: one step's ~600 activation /
+    scratch buffers come out of a few dozen identical 512 MiB blocks, so the allocator state is identical from step
+    to step (no fragmentation-driven cudaMalloc / cudaFree inside the timed region) and allocation costs no Python."""
+
+    CHUNK = 1 << 29
+
+    def __init__(self, dev):
+        self.dev, self.chunks, self.cur, self.off = dev, [], None, 0
+
+    def alloc(self, *shape, dtype=BF16, dev=None):
+        n = 1
+        for s_ in shape:
+            n *= int(s_)
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        aligned = (nbytes + 255) & ~255
+        if self.cur is None or self.off + aligned > self.cur.numel():
+            self.cur = torch.empty(max(self.CHUNK, aligned), dtype=torch.uint8, device=self.dev)
+            self.chunks.append(self.cur)
+            self.off = 0
+        t = self.cur[self.off:self.off + nbytes].view(dtype).view(*shape)
+        self.off += aligned
+        return t
+
+    def zeros(self, *shape, dtype=F32):
+        t = self.alloc(*shape, dtype=dtype)
+        t.zero_()
+        return t
+
+
 class _WeightCache:
     """bf16 operand copies of the fp32 master weights in the kernels' layouts, refreshed when a parameter changes
     (`Tensor._version` bumps on every in-place optimizer update)."""
@@ -335,6 +365,8 @@ class _EncoderFn(torch.autograd.Function):
         p_att = enc.dropout_att if training else 0.0
         W = enc._weights()
         S = {}  # saved activations
+        arena = _Arena(dev)
+        _empty = arena.alloc  # noqa: F811  (all activations of this step live in the arena kept by ctx)
 
         # ---- lengths (subsampling.py:576-586) ---------------------------------------------------------------
         len_in32 = _empty(B, dtype=torch.int32, dev=dev)
@@ -429,7 +461,7 @@ class _EncoderFn(torch.autograd.Function):
                   rows_per_batch=T)
             c = _empty(M, d, dev=dev)
             bn = cv.batch_norm
-            stats = torch.zeros(2, d, dtype=F32, device=dev)
+            stats = arena.zeros(2, d)
             L.call("dwconv_fwd", u, cv.depthwise_conv.weight.detach(), cv.depthwise_conv.bias.detach(), c,
                    stats[0] if training else None, stats[1] if training else None, B, T, d, k)
             bnp = _empty(4, d, dtype=F32, dev=dev)  # scale, shift, mean, rstd
@@ -449,7 +481,7 @@ class _EncoderFn(torch.autograd.Function):
             layers_saved.append(sv)
             x = xo
 
-        ctx.enc, ctx.S, ctx.layers_saved, ctx.W = enc, S, layers_saved, W
+        ctx.enc, ctx.S, ctx.layers_saved, ctx.W, ctx.arena = enc, S, layers_saved, W, arena
         ctx.meta = dict(B=B, T=T, M=M, Ts=Ts, Fs=Fs, seed=seed, p_drop=p_drop, p_pre=p_pre, p_att=p_att, training=training,
                         mel=mel, len_in32=len_in32, lens=lens, pos16=pos16, xlast=xlast, nparams=len(params))
         ctx.mark_non_differentiable(out_len)
@@ -489,6 +521,8 @@ class _EncoderFn(torch.autograd.Function):
                 G[n] = flat[off:off + sz].view_as(p)
                 off += sz
 
+        arena = _Arena(dev)
+        _empty = arena.alloc  # noqa: F811
         dr = dout.transpose(1, 2).contiguous().view(M, d).to(F32)
         t16 = _empty(M, d, dev=dev)
 
@@ -530,7 +564,7 @@ class _EncoderFn(torch.autograd.Function):
             L.call("colsum_bf16", t16, G[pfx + "conv.pointwise_conv2.bias"], M, d, d)
             ds = _empty(M, d, dev=dev)
             _gemm(t16, W[f"{li}.pw2"], M, d, d, L.EPI_BF16, b_mn=1, ldb=d, out0=ds)
-            sums = torch.zeros(2, d, dtype=F32, device=dev)
+            sums = arena.zeros(2, d)
             L.call("bn_silu_bwd_reduce", ds, c, bnp[0], bnp[1], bnp[2], bnp[3], sums[0], sums[1], M, d)
             dc = _empty(M, d, dev=dev)
             L.call("bn_silu_bwd_apply", ds, c, cv.batch_norm.weight.detach(), bnp[0], bnp[1], bnp[2], bnp[3], sums[0],
@@ -541,10 +575,10 @@ class _EncoderFn(torch.autograd.Function):
                    G[pfx + "conv.depthwise_conv.weight"], G[pfx + "conv.depthwise_conv.bias"], B, T, d, k)
             dg = _empty(M, 2 * d, dev=dev)
             L.call("glu_bwd", du, g, dg, M, d)
-            gw = torch.zeros(2 * d, d, dtype=F32, device=dev)  # interleaved layout
+            gw = arena.zeros(2 * d, d)  # interleaved layout
             wgrad(dg, 2 * d, y3, d, gw)
             _permute_f32(gw, d, 2, d, 0, out=G[pfx + "conv.pointwise_conv1.weight"], accumulate=1)
-            gb = torch.zeros(2 * d, dtype=F32, device=dev)
+            gb = arena.zeros(2 * d)
             L.call("colsum_bf16", dg, gb, M, 2 * d, 2 * d)
             _permute_f32(gb, d, 2, 1, 0, out=G[pfx + "conv.pointwise_conv1.bias"], accumulate=1)
             dy3 = _empty(M, d, dev=dev)
@@ -558,7 +592,7 @@ class _EncoderFn(torch.autograd.Function):
             dctx = _empty(M, d, dev=dev)
             _gemm(t16, W[f"{li}.o"], M, d, d, L.EPI_BF16, b_mn=1, ldb=d, out0=dctx)
             dqkv = _empty(M, 3 * d, dev=dev)
-            dpos = torch.zeros(2 * T - 1, d, dtype=F32, device=dev)
+            dpos = arena.zeros(2 * T - 1, d)
             nbytes = L.lib.b2c_relpos_attn_bwd_workspace(B, T, H)
             ws = enc.__dict__.get("_attn_ws")
             if ws is None or ws.numel() < nbytes or ws.device != dev:
@@ -567,9 +601,9 @@ class _EncoderFn(torch.autograd.Function):
             L.call("relpos_attn_bwd", qkv, pp, at.pos_bias_u.detach(), at.pos_bias_v.detach(), mt["lens"][-1], ctxv, dctx, lse,
                    dqkv, dpos, G[pfx + "self_attn.pos_bias_u"], G[pfx + "self_attn.pos_bias_v"], ws, nbytes, B, T, H, dk,
                    p_att, seed, site + S_ATT_P)
-            gqkv = torch.zeros(3 * d, d, dtype=F32, device=dev)
+            gqkv = arena.zeros(3 * d, d)
             wgrad(dqkv, 3 * d, y2, d, gqkv)
-            gqb = torch.zeros(3 * d, dtype=F32, device=dev)
+            gqb = arena.zeros(3 * d)
             L.call("colsum_bf16", dqkv, gqb, M, 3 * d, 3 * d)
             for j, nm in enumerate(("linear_q", "linear_k", "linear_v")):
                 G[f"{pfx}self_attn.{nm}.weight"].add_(gqkv[j * d:(j + 1) * d])
@@ -590,7 +624,7 @@ class _EncoderFn(torch.autograd.Function):
         # ---- pre_encode: xscale + dropout backward, out Linear, convolutions
         L.call("scale_drop_cast", dr, t16, M * d, enc.xscale or 1.0, p_pre, seed, enc.n_layers * 16)
         xlast = mt["xlast"]
-        gw = torch.zeros(d, F2 * C, dtype=F32, device=dev)
+        gw = arena.zeros(d, F2 * C)
         wgrad(t16, d, xlast.view(M, F2 * C), F2 * C, gw)
         _permute_f32(gw, d, F2, C, 1, out=G["pre_encode.out.weight"], accumulate=1)
         L.call("colsum_bf16", t16, G["pre_encode.out.bias"], M, d, d)
@@ -599,7 +633,7 @@ class _EncoderFn(torch.autograd.Function):
         Ts, Fs, lens = mt["Ts"], mt["Fs"], mt["lens"]
         if enc.subsampling == "striding":
             x1, x2 = ctx.S["sub"]
-            gw2 = torch.zeros(C, 9 * C, dtype=F32, device=dev)
+            gw2 = arena.zeros(C, 9 * C)
             L.call("conv3x3s2_bwd_weight", dylast, x1, gw2, B, Ts[1], Fs[1], C)
             _permute_f32(gw2, C, 9, C, 1, out=G["pre_encode.conv.2.weight"], accumulate=1)
             L.call("colsum_bf16", dylast, G["pre_encode.conv.2.bias"], B * Ts[2] * Fs[2], C, C)
