@@ -674,7 +674,7 @@ relpos_attn_bwd_pos_kernel(const AttnArgs a, const bf16* __restrict__ ws_ds, flo
             uint32_t prev = w[0];
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-              const uint32_t nxt = (k < 15 || js + 32 < Tp) ? w[k + 1] : 0u;
+              const uint32_t nxt = (k < 15) ? w[k + 1] : (uint32_t)reinterpret_cast<const uint16_t*>(src)[31];
               dst[k] = __funnelshift_r(prev, nxt, 16);
               prev = nxt;
             }
