@@ -40,10 +40,11 @@ dwconv_fwd_kernel(const bf16* __restrict__ u, const float* __restrict__ w, const
     const int t0 = (blockIdx.y * tiles_per_cta + tile) * kTT;
     if (t0 >= T) break;
     __syncthreads();
-    for (int r = 0; r < kTT + K - 1; ++r) {
+#pragma unroll 16
+    for (int r = 0; r < kTT + K - 1; ++r) {  // unrolled so the independent global loads are in flight together
       const int t = t0 + r - PAD;
       uint32_t v = 0u;
-      if (act && t >= 0 && t < T) v = *reinterpret_cast<const uint32_t*>(ub + (size_t)t * d + ch);
+      if (act && t >= 0 && t < T) v = __ldg(reinterpret_cast<const uint32_t*>(ub + (size_t)t * d + ch));
       su[r * 128 + threadIdx.x] = v;
     }
     __syncthreads();
@@ -203,12 +204,13 @@ dwconv_bwd_kernel(const bf16* __restrict__ dc, const bf16* __restrict__ u, const
     const int t0 = (blockIdx.y * tiles_per_cta + tile) * kTT;
     if (t0 >= T) break;
     __syncthreads();
+#pragma unroll 8
     for (int r = 0; r < ROWS; ++r) {
       const int t = t0 + r - PAD;
       uint32_t a = 0u, bb = 0u;
       if (act && t >= 0 && t < T) {
-        a = *reinterpret_cast<const uint32_t*>(dcb + (size_t)t * d + ch);
-        bb = *reinterpret_cast<const uint32_t*>(ub + (size_t)t * d + ch);
+        a = __ldg(reinterpret_cast<const uint32_t*>(dcb + (size_t)t * d + ch));
+        bb = __ldg(reinterpret_cast<const uint32_t*>(ub + (size_t)t * d + ch));
       }
       sdc[r * 128 + threadIdx.x] = a;
       suu[r * 128 + threadIdx.x] = bb;

@@ -24,8 +24,8 @@ namespace b2c {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int kNumThreads = 384;  // 4 role warps + 8 epilogue warps
 constexpr int kEpiWarps = 8;
+constexpr int kNumThreads = 128 + 32 * kEpiWarps;  // 4 role warps + 8 epilogue warps
 
 // Implicit-GEMM geometry of the 3x3 stride-2 subsampling convolution (no im2col is ever materialised: the
 // A tiles are gathered by 4-D TMA boxes, strided for the forward / weight-gradient, shifted for the data-gradient).
@@ -54,7 +54,8 @@ struct SmemLayout {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kTotal = kBarOffset + 256 + 1024;  // + barriers + alignment slack
+  static constexpr int kStageOut = kBarOffset + 256;                 // per-epilogue-warp 4 KB output staging
+  static constexpr int kTotal = kStageOut + kEpiWarps * 4096 + 1024;  // + alignment slack
 };
 
 // ---------------------------------------------------------------- epilogue
@@ -246,6 +247,151 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
   }
 }
 
+// ---------------------------------------------------------------- coalesced output through a per-warp smem stage
+// Each thread owns one accumulator ROW (TMEM lane), which would make every global store instruction touch 32 rows
+// (half-filled sectors).  The 32x32 chunk is bounced through a 4 KB swizzled shared-memory tile so each store
+// instruction writes whole 64 B / 128 B row segments.  m_lane = global output row of this lane (>= M: skip).
+__device__ __forceinline__ void stage_store_bf16(uint8_t* stg, int lane, const float (&v)[32], bf16* out, size_t ldo,
+                                                 int m_lane, int M, int n0) {
+  __syncwarp();
+  const int f = (lane >> 1) & 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    *reinterpret_cast<uint4*>(stg + lane * 64 + ((k ^ f) << 4)) =
+        make_uint4(pack_bf16(v[8 * k], v[8 * k + 1]), pack_bf16(v[8 * k + 2], v[8 * k + 3]),
+                   pack_bf16(v[8 * k + 4], v[8 * k + 5]), pack_bf16(v[8 * k + 6], v[8 * k + 7]));
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 8 + (lane >> 2), ck = lane & 3;
+    const int m = __shfl_sync(0xffffffffu, m_lane, row);
+    const uint4 q = *reinterpret_cast<const uint4*>(stg + row * 64 + ((ck ^ ((row >> 1) & 3)) << 4));
+    if (m < M) *reinterpret_cast<uint4*>(out + (size_t)m * ldo + n0 + ck * 8) = q;
+  }
+}
+// out_f32[m, n0..n0+31] = (aux ? aux[m, ...] : 0) + v   (v already scaled)
+__device__ __forceinline__ void stage_store_f32(uint8_t* stg, int lane, const float (&v)[32], float* out, const float* aux,
+                                                size_t ldo, int m_lane, int M, int n0) {
+  __syncwarp();
+  const int f = lane & 7;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ f) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + (lane >> 3), ck = lane & 7;
+    const int m = __shfl_sync(0xffffffffu, m_lane, row);
+    float4 q = *reinterpret_cast<const float4*>(stg + row * 128 + ((ck ^ (row & 7)) << 4));
+    if (m < M) {
+      const size_t o = (size_t)m * ldo + n0 + ck * 4;
+      if (aux) {
+        const float4 r = *reinterpret_cast<const float4*>(aux + o);
+        q.x += r.x; q.y += r.y; q.z += r.z; q.w += r.w;
+      }
+      *reinterpret_cast<float4*>(out + o) = q;
+    }
+  }
+}
+
+// Warp-collective epilogue of one 32-row x 32-column chunk.  Falls back to the per-thread path for ragged N.
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int n0, int M, int N, const uint32_t (&acc)[32],
+                                               bool atomic, uint8_t* stg, int lane) {
+  if (n0 >= N) return;  // warp-uniform
+  const bool full = (n0 + 32 <= N);
+  constexpr bool kStaged = (MODE == B2C_EPI_BF16 || MODE == B2C_EPI_SILU || MODE == B2C_EPI_RESID_F32 ||
+                            MODE == B2C_EPI_DSILU || MODE == B2C_EPI_RELU_MASK || MODE == B2C_EPI_RELU_BWD ||
+                            MODE == B2C_EPI_GLU_MASK);
+  if (!kStaged || !full) {
+    epilogue_row<MODE>(e, m, n0, M, N, acc, atomic);
+    return;
+  }
+  const bool rowok = m < M;
+  const int ms = rowok ? m : 0;  // safe row for loads of invalid lanes
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  if (MODE != B2C_EPI_RELU_BWD && MODE != B2C_EPI_DSILU && e.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(e.bias + n0 + j);
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  const size_t ldo = (size_t)e.ldo;
+  const uint64_t didx = (uint64_t)ms * (uint64_t)N + (uint64_t)n0;
+  if (MODE == B2C_EPI_BF16) {
+    stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
+  } else if (MODE == B2C_EPI_SILU) {
+    float h[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      v[j] = bf16_round(v[j]);
+      h[j] = silu_f(v[j]);
+    }
+    if (e.drop_keep != 0) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) h[j] = bf16_round(h[j]);
+      dropout32(h, e, didx);
+    }
+    stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
+    stage_store_bf16(stg, lane, h, reinterpret_cast<bf16*>(e.out1), ldo, m, M, n0);
+  } else if (MODE == B2C_EPI_RESID_F32) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
+    if (e.drop_keep != 0) dropout32(v, e, didx);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
+    stage_store_f32(stg, lane, v, reinterpret_cast<float*>(e.out0), reinterpret_cast<const float*>(e.aux), ldo, m, M, n0);
+  } else if (MODE == B2C_EPI_GLU_MASK) {
+    bool valid = rowok;
+    if (e.lengths && rowok) {
+      const int b = m / e.rows_per_batch, t = m - b * e.rows_per_batch;
+      valid = t < e.lengths[b];
+    }
+    float u[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      v[j] = bf16_round(v[j]);
+      v[j + 1] = bf16_round(v[j + 1]);
+      u[j >> 1] = valid ? v[j] * sigmoid_f(v[j + 1]) : 0.f;
+    }
+    stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
+    if (rowok) {
+      bf16* ou = reinterpret_cast<bf16*>(e.out1) + (size_t)m * (ldo >> 1) + (n0 >> 1);
+#pragma unroll
+      for (int j = 0; j < 16; j += 8)
+        *reinterpret_cast<uint4*>(ou + j) = make_uint4(pack_bf16(u[j], u[j + 1]), pack_bf16(u[j + 2], u[j + 3]),
+                                                       pack_bf16(u[j + 4], u[j + 5]), pack_bf16(u[j + 6], u[j + 7]));
+    }
+  } else if (MODE == B2C_EPI_DSILU) {
+    float zz[32];
+    load_bf16x32(reinterpret_cast<const bf16*>(e.aux) + (size_t)ms * ldo + n0, zz);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
+    if (e.drop_keep != 0) dropout32(v, e, didx);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= dsilu_f(zz[j]);
+    stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
+  } else if (MODE == B2C_EPI_RELU_MASK) {
+    bool valid = rowok;
+    if (e.lengths && rowok) {
+      const int b = m / e.rows_per_batch, t = (m - b * e.rows_per_batch) / e.rows_inner;
+      valid = t < e.lengths[b];
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = valid ? fmaxf(v[j], 0.f) : 0.f;
+    stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
+  } else if (MODE == B2C_EPI_RELU_BWD) {
+    float yy[32];
+    load_bf16x32(reinterpret_cast<const bf16*>(e.aux) + (size_t)ms * ldo + n0, yy);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = yy[j] > 0.f ? v[j] : 0.f;
+    stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
+  }
+}
+
 // ---------------------------------------------------------------- kernel
 // CONV: 0 = plain GEMM; 1 = conv forward (strided gather A); 2 = conv data-gradient (shifted gather A, scatter rows);
 //       3 = conv weight-gradient (tokens are the contraction; A = dY, B = strided gather of X, one tap per `split`)
@@ -380,6 +526,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {
     const int q = warp & 3;             // TMEM lane quarter this warp may access (= warp id % 4)
     const int chalf = (warp - 4) >> 2;  // two warps share a quarter and split the 32-column chunks
+    uint8_t* stg = smem + L::kStageOut + (warp - 4) * 4096;
     int as = 0, aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mn = tile / p.splits;
@@ -405,7 +552,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t acc[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), acc);
         tmem_ld_wait();
-        epilogue_row<MODE>(epi, m, n0 + c * 32, m_bound, p.N, acc, CONV == 0 && p.splits > 1);
+        epilogue_chunk<MODE>(epi, m, n0 + c * 32, m_bound, p.N, acc, CONV == 0 && p.splits > 1, stg, lane);
       }
       tc_fence_before();
       __syncwarp();

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Full GPU check: pytest -m gpu, smoke(), bench (ours), ncu launch list of one bench step.
 mkdir -p gpurun_out
-( timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -25 ) | tee gpurun_out/pytest_gpu.log
+timeout 1500 python -m pytest tests -m gpu -q -s > gpurun_out/pytest_full.log 2>&1; grep -E "FAIL|passed|failed|Error" gpurun_out/pytest_full.log | tail -25 | tee gpurun_out/pytest_gpu.log
 ( timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 ) | tee gpurun_out/smoke.log
 ( timeout 900 python bench.py --steps ${STEPS:-5} --warmup 3 2>&1 | tail -5 ) | tee gpurun_out/bench.log
 if [ "${NCU:-1}" = "1" ]; then
