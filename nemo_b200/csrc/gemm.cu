@@ -278,19 +278,23 @@ __device__ __forceinline__ void stage_store_f32(uint8_t* stg, int lane, const fl
   for (int k = 0; k < 8; ++k)
     *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ f) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
   __syncwarp();
+  // all residual loads first (out / aux may alias as far as the compiler knows, which would serialise them)
+  float4 r[8];
+  int mm[8];
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int row = it * 4 + (lane >> 3), ck = lane & 7;
-    const int m = __shfl_sync(0xffffffffu, m_lane, row);
-    float4 q = *reinterpret_cast<const float4*>(stg + row * 128 + ((ck ^ (row & 7)) << 4));
-    if (m < M) {
-      const size_t o = (size_t)m * ldo + n0 + ck * 4;
-      if (aux) {
-        const float4 r = *reinterpret_cast<const float4*>(aux + o);
-        q.x += r.x; q.y += r.y; q.z += r.z; q.w += r.w;
-      }
-      *reinterpret_cast<float4*>(out + o) = q;
-    }
+    mm[it] = __shfl_sync(0xffffffffu, m_lane, row);
+    r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (aux && mm[it] < M) r[it] = __ldg(reinterpret_cast<const float4*>(aux + (size_t)mm[it] * ldo + n0 + ck * 4));
+  }
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + (lane >> 3), ck = lane & 7;
+    const float4 q = *reinterpret_cast<const float4*>(stg + row * 128 + ((ck ^ (row & 7)) << 4));
+    if (mm[it] < M)
+      *reinterpret_cast<float4*>(out + (size_t)mm[it] * ldo + n0 + ck * 4) =
+          make_float4(q.x + r[it].x, q.y + r[it].y, q.z + r[it].z, q.w + r[it].w);
   }
 }
 
