@@ -138,14 +138,16 @@ int b2c_glu_bwd(const void* du_bf16, const void* g_bf16, void* dg_bf16, long lon
  * Transformer-XL relative-position attention, flash-style (nothing [T,T]-shaped touches HBM):
  *   S[i,j] = ((q_i+u).k_j + (q_i+v).p[T-1-i+j]) / sqrt(dk);  masked_fill(-1e4); softmax; masked_fill(0); dropout; PV
  * (multi_head_attention.py:125-146,259-354).  qkv [B*T, 3*d] bf16 (q | k | v), pos [2T-1, d] bf16,
- * pos_bias_u/v [h, dk] f32, lengths [B] i32.  ctx [B*T, d] bf16, lse [B, h, T] f32. */
+ * pos_bias_u/v [h, dk] f32, lengths [B] i32.  ctx [B*T, d] bf16, lse [B, h, T] f32 (base-2 log-sum-exp).
+ * ctx_f32 (optional, [B*T, d] f32): un-rounded context kept for the backward's row term delta = sum(dO * O);
+ * with only the bf16 context the rounding error biases whole rows of dS when value rows are nearly identical. */
 int b2c_relpos_attn_fwd(const void* qkv, const void* pos, const float* bias_u, const float* bias_v,
-                        const int32_t* lengths, void* ctx, float* lse, int B, int T, int h, int dk, float drop_p,
-                        unsigned long long seed, unsigned int site, void* stream);
+                        const int32_t* lengths, void* ctx, float* ctx_f32, float* lse, int B, int T, int h, int dk,
+                        float drop_p, unsigned long long seed, unsigned int site, void* stream);
 size_t b2c_relpos_attn_bwd_workspace(int B, int T, int h);
 int b2c_relpos_attn_bwd(const void* qkv, const void* pos, const float* bias_u, const float* bias_v,
-                        const int32_t* lengths, const void* ctx, const void* dctx, const float* lse, void* dqkv,
-                        float* dpos_f32, float* dbias_u, float* dbias_v, void* workspace, size_t workspace_bytes,
+                        const int32_t* lengths, const void* ctx, const float* ctx_f32, const void* dctx, const float* lse,
+                        void* dqkv, float* dpos_f32, float* dbias_u, float* dbias_v, void* workspace, size_t workspace_bytes,
                         int B, int T, int h, int dk, float drop_p, unsigned long long seed, unsigned int site,
                         void* stream);
 

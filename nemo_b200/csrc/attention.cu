@@ -201,7 +201,7 @@ __device__ __forceinline__ bool attn_keep(const AttnArgs& a, int b, int h, int i
 // =============================================================================================== forward
 template <int DK>
 __global__ void __launch_bounds__(128)
-relpos_attn_fwd_kernel(const AttnArgs a, bf16* __restrict__ ctx, float* __restrict__ lse_out) {
+relpos_attn_fwd_kernel(const AttnArgs a, bf16* __restrict__ ctx, float* __restrict__ ctx32, float* __restrict__ lse_out) {
   constexpr int P = DK + 8;
   extern __shared__ __align__(16) uint8_t smraw[];
   constexpr int STAGE = (BKV + BKV + 128) * P;  // K, V, 128 band rows of P
@@ -318,6 +318,12 @@ relpos_attn_fwd_kernel(const AttnArgs a, bf16* __restrict__ ctx, float* __restri
 #pragma unroll
       for (int nt = 0; nt < DK / 8; ++nt)
         *reinterpret_cast<uint32_t*>(op + nt * 8 + 2 * c) = pack_bf16(o[nt][rr * 2] * inv, o[nt][rr * 2 + 1] * inv);
+      if (ctx32) {  // un-rounded copy for the backward's delta = rowsum(dO * O) (a bf16 O biases whole rows of dS)
+        float* o32 = ctx32 + ((size_t)b * T + row) * a.d + h * DK;
+#pragma unroll
+        for (int nt = 0; nt < DK / 8; ++nt)
+          *reinterpret_cast<float2*>(o32 + nt * 8 + 2 * c) = make_float2(o[nt][rr * 2] * inv, o[nt][rr * 2 + 1] * inv);
+      }
       if (c == 0 && lse_out) lse_out[((size_t)b * a.H + h) * T + row] = (row < len && l[rr] > 0.f) ? m[rr] + log2f(l[rr]) : 0.f;
     }
   }
@@ -328,7 +334,8 @@ relpos_attn_fwd_kernel(const AttnArgs a, bf16* __restrict__ ctx, float* __restri
 // stages dS (scaled, bf16) and P_dropped (bf16) in HBM workspaces [B,H,T,Tp] for the key-side / position-side kernels.
 template <int DK>
 __global__ void __launch_bounds__(128)
-relpos_attn_bwd_q_kernel(const AttnArgs a, const bf16* __restrict__ ctx, const bf16* __restrict__ dctx,
+relpos_attn_bwd_q_kernel(const AttnArgs a, const bf16* __restrict__ ctx, const float* __restrict__ ctx32,
+                         const bf16* __restrict__ dctx,
                          const float* __restrict__ lse, bf16* __restrict__ dqkv, float* __restrict__ dbias_u,
                          float* __restrict__ dbias_v, bf16* __restrict__ ws_ds, bf16* __restrict__ ws_p, int Tp) {
   constexpr int P = DK + 8;
@@ -362,9 +369,11 @@ relpos_attn_bwd_q_kernel(const AttnArgs a, const bf16* __restrict__ ctx, const b
     if (row < T) {
       const bf16* op = ctx + ((size_t)b * T + row) * a.d + h * DK;
       const bf16* dp = dctx + ((size_t)b * T + row) * a.d + h * DK;
+      const float* o32 = ctx32 ? ctx32 + ((size_t)b * T + row) * a.d + h * DK : nullptr;
 #pragma unroll
       for (int nt = 0; nt < DK / 8; ++nt) {
-        const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(op + nt * 8 + 2 * c));
+        const float2 x = o32 ? *reinterpret_cast<const float2*>(o32 + nt * 8 + 2 * c)
+                             : unpack_bf16(*reinterpret_cast<const uint32_t*>(op + nt * 8 + 2 * c));
         const float2 y = unpack_bf16(*reinterpret_cast<const uint32_t*>(dp + nt * 8 + 2 * c));
         acc += x.x * y.x + x.y * y.y;
       }
@@ -736,20 +745,20 @@ template <int DK>
 static size_t smem_q() { return (size_t)2 * (64 + 64 + 128) * (DK + 8) * 2 + 4 * 16 * SCR_PITCH * 4; }
 
 template <int DK>
-static int launch_fwd(const AttnArgs& a, bf16* ctx, float* lse, cudaStream_t st) {
+static int launch_fwd(const AttnArgs& a, bf16* ctx, float* ctx32, float* lse, cudaStream_t st) {
   const size_t smem = smem_q<DK>();
   static bool set = false;
   if (!set) {
     B2C_CUDA(cudaFuncSetAttribute(relpos_attn_fwd_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     set = true;
   }
-  relpos_attn_fwd_kernel<DK><<<dim3((a.T + BQ - 1) / BQ, a.H, a.B), 128, smem, st>>>(a, ctx, lse);
+  relpos_attn_fwd_kernel<DK><<<dim3((a.T + BQ - 1) / BQ, a.H, a.B), 128, smem, st>>>(a, ctx, ctx32, lse);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
 }
 
 template <int DK>
-static int launch_bwd(const AttnArgs& a, const bf16* ctx, const bf16* dctx, const float* lse, bf16* dqkv, float* dpos,
+static int launch_bwd(const AttnArgs& a, const bf16* ctx, const float* ctx32, const bf16* dctx, const float* lse, bf16* dqkv, float* dpos,
                       float* dbu, float* dbv, bf16* ws_ds, bf16* ws_p, int Tp, cudaStream_t st) {
   const size_t smem1 = smem_q<DK>();
   const size_t smem2 = 2 * ((size_t)2 * 64 * (DK + 8) * 2 + (size_t)2 * 64 * (BKV + 8) * 2);
@@ -762,7 +771,7 @@ static int launch_bwd(const AttnArgs& a, const bf16* ctx, const bf16* dctx, cons
     set = true;
   }
   const int qt = (a.T + BQ - 1) / BQ;
-  relpos_attn_bwd_q_kernel<DK><<<dim3(qt, a.H, a.B), 128, smem1, st>>>(a, ctx, dctx, lse, dqkv, dbu, dbv, ws_ds, ws_p, Tp);
+  relpos_attn_bwd_q_kernel<DK><<<dim3(qt, a.H, a.B), 128, smem1, st>>>(a, ctx, ctx32, dctx, lse, dqkv, dbu, dbv, ws_ds, ws_p, Tp);
   B2C_LAUNCH_CHECK();
   relpos_attn_bwd_kv_kernel<DK><<<dim3(qt, a.H, a.B), 128, smem2, st>>>(a, dctx, ws_ds, ws_p, dqkv, Tp);
   B2C_LAUNCH_CHECK();
@@ -778,13 +787,13 @@ static int launch_bwd(const AttnArgs& a, const bf16* ctx, const bf16* dctx, cons
 using namespace b2c;
 
 extern "C" int b2c_relpos_attn_fwd(const void* qkv, const void* pos, const float* bias_u, const float* bias_v,
-                                   const int32_t* lengths, void* ctx, float* lse, int B, int T, int h, int dk,
-                                   float drop_p, unsigned long long seed, unsigned int site, void* stream) {
+                                   const int32_t* lengths, void* ctx, float* ctx_f32, float* lse, int B, int T, int h,
+                                   int dk, float drop_p, unsigned long long seed, unsigned int site, void* stream) {
   AttnArgs a;
   int rc = fill_args(a, qkv, pos, bias_u, bias_v, lengths, B, T, h, dk, drop_p, seed, site);
   if (rc) return rc;
-  if (dk == 64) return launch_fwd<64>(a, reinterpret_cast<bf16*>(ctx), lse, (cudaStream_t)stream);
-  return launch_fwd<128>(a, reinterpret_cast<bf16*>(ctx), lse, (cudaStream_t)stream);
+  if (dk == 64) return launch_fwd<64>(a, reinterpret_cast<bf16*>(ctx), ctx_f32, lse, (cudaStream_t)stream);
+  return launch_fwd<128>(a, reinterpret_cast<bf16*>(ctx), ctx_f32, lse, (cudaStream_t)stream);
 }
 
 /* workspace: 2 * B*h*T*Tp bf16 with Tp = (T+7)&~7 */
@@ -794,8 +803,8 @@ extern "C" size_t b2c_relpos_attn_bwd_workspace(int B, int T, int h) {
 }
 
 extern "C" int b2c_relpos_attn_bwd(const void* qkv, const void* pos, const float* bias_u, const float* bias_v,
-                                   const int32_t* lengths, const void* ctx, const void* dctx, const float* lse,
-                                   void* dqkv, float* dpos_f32, float* dbias_u, float* dbias_v, void* workspace,
+                                   const int32_t* lengths, const void* ctx, const float* ctx_f32, const void* dctx,
+                                   const float* lse, void* dqkv, float* dpos_f32, float* dbias_u, float* dbias_v, void* workspace,
                                    size_t workspace_bytes, int B, int T, int h, int dk, float drop_p,
                                    unsigned long long seed, unsigned int site, void* stream) {
   AttnArgs a;
@@ -806,8 +815,8 @@ extern "C" int b2c_relpos_attn_bwd(const void* qkv, const void* pos, const float
   bf16* ws_ds = reinterpret_cast<bf16*>(workspace);
   bf16* ws_p = ws_ds + (size_t)B * h * T * Tp;
   if (dk == 64)
-    return launch_bwd<64>(a, reinterpret_cast<const bf16*>(ctx), reinterpret_cast<const bf16*>(dctx), lse,
+    return launch_bwd<64>(a, reinterpret_cast<const bf16*>(ctx), ctx_f32, reinterpret_cast<const bf16*>(dctx), lse,
                           reinterpret_cast<bf16*>(dqkv), dpos_f32, dbias_u, dbias_v, ws_ds, ws_p, Tp, (cudaStream_t)stream);
-  return launch_bwd<128>(a, reinterpret_cast<const bf16*>(ctx), reinterpret_cast<const bf16*>(dctx), lse,
+  return launch_bwd<128>(a, reinterpret_cast<const bf16*>(ctx), ctx_f32, reinterpret_cast<const bf16*>(dctx), lse,
                          reinterpret_cast<bf16*>(dqkv), dpos_f32, dbias_u, dbias_v, ws_ds, ws_p, Tp, (cudaStream_t)stream);
 }

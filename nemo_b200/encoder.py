@@ -446,12 +446,13 @@ class _EncoderFn(torch.autograd.Function):
             _gemm(pos16, W[f"{li}.pos"], 2 * T - 1, d, d, L.EPI_BF16, out0=pp)
             ctxv = _empty(M, d, dev=dev)
             lse = _empty(B, H, T, dtype=F32, dev=dev)
-            L.call("relpos_attn_fwd", qkv, pp, at.pos_bias_u.detach(), at.pos_bias_v.detach(), enc_len32, ctxv, lse, B, T,
-                   H, dk, p_att, seed, site + S_ATT_P)
+            ctx32 = _empty(M, d, dtype=F32, dev=dev) if training else None
+            L.call("relpos_attn_fwd", qkv, pp, at.pos_bias_u.detach(), at.pos_bias_v.detach(), enc_len32, ctxv, ctx32, lse,
+                   B, T, H, dk, p_att, seed, site + S_ATT_P)
             xb = _empty(M, d, dtype=F32, dev=dev)
             _gemm(ctxv, W[f"{li}.o"], M, d, d, L.EPI_RESID_F32, out0=xb, aux=xa, bias=at.linear_out.bias.detach(), alpha=1.0,
                   seed=seed, drop_site=site + S_ATT_OUT, drop_p=p_drop)
-            sv["att"] = (xa, y2, m2, r2, qkv, pp, ctxv, lse)
+            sv["att"] = (xa, y2, m2, r2, qkv, pp, ctxv, lse, ctx32)
             # convolution module
             cv = lyr.conv
             y3, m3, r3 = ln(xb, lyr.norm_conv)
@@ -585,7 +586,7 @@ class _EncoderFn(torch.autograd.Function):
             _gemm(dg, W[f"{li}.pw1"], M, d, 2 * d, L.EPI_BF16, b_mn=1, ldb=d, out0=dy3)
             ln_bwd(dy3, 1, xb, pfx + "norm_conv", lyr.norm_conv, m3, r3, 1, t16, 1.0, site + S_ATT_OUT, p_drop)
             # ---- self-attention (t16 = gradient of linear_out's output)
-            xa, y2, m2, r2, qkv, pp, ctxv, lse = sv["att"]
+            xa, y2, m2, r2, qkv, pp, ctxv, lse, ctx32 = sv["att"]
             at = lyr.self_attn
             wgrad(t16, d, ctxv, d, G[pfx + "self_attn.linear_out.weight"])
             L.call("colsum_bf16", t16, G[pfx + "self_attn.linear_out.bias"], M, d, d)
@@ -598,7 +599,7 @@ class _EncoderFn(torch.autograd.Function):
             if ws is None or ws.numel() < nbytes or ws.device != dev:
                 ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
                 enc.__dict__["_attn_ws"] = ws
-            L.call("relpos_attn_bwd", qkv, pp, at.pos_bias_u.detach(), at.pos_bias_v.detach(), mt["lens"][-1], ctxv, dctx, lse,
+            L.call("relpos_attn_bwd", qkv, pp, at.pos_bias_u.detach(), at.pos_bias_v.detach(), mt["lens"][-1], ctxv, ctx32, dctx, lse,
                    dqkv, dpos, G[pfx + "self_attn.pos_bias_u"], G[pfx + "self_attn.pos_bias_v"], ws, nbytes, B, T, H, dk,
                    p_att, seed, site + S_ATT_P)
             gqkv = arena.zeros(3 * d, d)

@@ -323,7 +323,8 @@ def test_relpos_attention_fwd_bwd(B, T, h, dk):
     bu, bv = rnd(h, dk, scale=0.3, seed=4), rnd(h, dk, scale=0.3, seed=5)
     ctx = torch.empty(B * T, d, dtype=torch.bfloat16, device=DEV)
     lse = torch.empty(B, h, T, device=DEV)
-    L.call("relpos_attn_fwd", qkv16, pos16, bu, bv, lengths, ctx, lse, B, T, h, dk, 0.0, 0, 0)
+    ctx32 = torch.empty(B * T, d, device=DEV)
+    L.call("relpos_attn_fwd", qkv16, pos16, bu, bv, lengths, ctx, ctx32, lse, B, T, h, dk, 0.0, 0, 0)
     qkvf = qkv16.float().view(B, T, 3, h, dk)
     q = qkvf[:, :, 0].clone().requires_grad_(True)
     k = qkvf[:, :, 1].clone().requires_grad_(True)
@@ -343,7 +344,7 @@ def test_relpos_attention_fwd_bwd(B, T, h, dk):
     dbu, dbv = torch.zeros(h, dk, device=DEV), torch.zeros(h, dk, device=DEV)
     nbytes = L.lib.b2c_relpos_attn_bwd_workspace(B, T, h)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
-    L.call("relpos_attn_bwd", qkv16, pos16, bu, bv, lengths, ctx, dctx16, lse, dqkv, dpos, dbu, dbv, ws, nbytes, B, T,
+    L.call("relpos_attn_bwd", qkv16, pos16, bu, bv, lengths, ctx, ctx32, dctx16, lse, dqkv, dpos, dbu, dbv, ws, nbytes, B, T,
            h, dk, 0.0, 0, 0)
     g = dqkv.float().view(B, T, 3, h, dk)
     report("attn_bwd_dq", g[:, :, 0], q.grad, 3e-2)
@@ -365,7 +366,7 @@ def test_relpos_attention_dropout_statistics():
     for seed in (0, 1, 2, 3):
         ctx = torch.empty(B * T, d, dtype=torch.bfloat16, device=DEV)
         lse = torch.empty(B, h, T, device=DEV)
-        L.call("relpos_attn_fwd", qkv16, pos16, bu, bv, lengths, ctx, lse, B, T, h, dk, 0.1 if seed else 0.0, seed, 5)
+        L.call("relpos_attn_fwd", qkv16, pos16, bu, bv, lengths, ctx, None, lse, B, T, h, dk, 0.1 if seed else 0.0, seed, 5)
         outs.append(ctx.float())
     # dropout is unbiased: averaging a few seeds approaches the p=0 output; and differs per seed
     assert not torch.equal(outs[1], outs[2])
