@@ -65,7 +65,7 @@ struct DropArgs {
 
 // rows handled per warp are strided so each warp keeps per-column dgamma/dbeta partials in registers
 template <bool DY_BF16, int kMaxVec>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (kMaxVec <= 4) ? 3 : 2)
 layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dr,
                      int accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta, bf16* __restrict__ next16,
@@ -78,12 +78,6 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, 
   float4 ag[kMaxVec], ab[kMaxVec];
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i) ag[i] = ab[i] = make_float4(0, 0, 0, 0);
-  float4 g[kMaxVec];
-#pragma unroll
-  for (int i = 0; i < kMaxVec; ++i) {
-    const int c = i * 32 + lane;
-    g[i] = (c < nv) ? reinterpret_cast<const float4*>(gamma)[c] : make_float4(0, 0, 0, 0);
-  }
   for (int row = blockIdx.x * wpb + wib; row < M; row += gridDim.x * wpb) {
     const float mu = mean[row], rs = rstd[row];
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d);
@@ -106,7 +100,8 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, 
         dyv[i] = dv;
         ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
         ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
-        const float a0 = dv.x * g[i].x, a1 = dv.y * g[i].y, a2 = dv.z * g[i].z, a3 = dv.w * g[i].w;
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        const float a0 = dv.x * gm.x, a1 = dv.y * gm.y, a2 = dv.z * gm.z, a3 = dv.w * gm.w;
         s1 += a0 + a1 + a2 + a3;
         s2 += a0 * xh[i].x + a1 * xh[i].y + a2 * xh[i].z + a3 * xh[i].w;
       } else {
@@ -119,11 +114,12 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, 
     for (int i = 0; i < kMaxVec; ++i) {
       const int c = i * 32 + lane;
       if (c < nv) {
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
         float4 o;
-        o.x = rs * (dyv[i].x * g[i].x - s1 - xh[i].x * s2);
-        o.y = rs * (dyv[i].y * g[i].y - s1 - xh[i].y * s2);
-        o.z = rs * (dyv[i].z * g[i].z - s1 - xh[i].z * s2);
-        o.w = rs * (dyv[i].w * g[i].w - s1 - xh[i].w * s2);
+        o.x = rs * (dyv[i].x * gm.x - s1 - xh[i].x * s2);
+        o.y = rs * (dyv[i].y * gm.y - s1 - xh[i].y * s2);
+        o.z = rs * (dyv[i].z * gm.z - s1 - xh[i].z * s2);
+        o.w = rs * (dyv[i].w * gm.w - s1 - xh[i].w * s2);
         float4* drp = reinterpret_cast<float4*>(dr + (size_t)row * d) + c;
         if (accumulate) {
           float4 p = *drp;
