@@ -24,8 +24,8 @@ namespace b2c {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int kEpiWarps = 8;
-constexpr int kNumThreads = 128 + 32 * kEpiWarps;  // 4 role warps + 8 epilogue warps
+constexpr int kEpiWarps = 16;
+constexpr int kNumThreads = 128 + 32 * kEpiWarps;  // 4 role warps + 16 epilogue warps
 
 // Implicit-GEMM geometry of the 3x3 stride-2 subsampling convolution (no im2col is ever materialised: the
 // A tiles are gathered by 4-D TMA boxes, strided for the forward / weight-gradient, shifted for the data-gradient).
@@ -54,344 +54,252 @@ struct SmemLayout {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kStageOut = kBarOffset + 256;                 // per-epilogue-warp 4 KB output staging
-  static constexpr int kTotal = kStageOut + kEpiWarps * 4096 + 1024;  // + alignment slack
+  static constexpr int kStageOut = kBarOffset + 256;                 // per-epilogue-warp 2 KB output staging
+  static constexpr int kTotal = kStageOut + kEpiWarps * 2048 + 1024;  // + alignment slack
 };
 
 // ---------------------------------------------------------------- epilogue
-// Each call handles one accumulator row `m`, 32 consecutive columns starting at n0 (n0 % 32 == 0).
-__device__ __forceinline__ void store_bf16x32(bf16* o, const float (&v)[32]) {
+// 16 epilogue warps (4 per TMEM lane quarter); each step handles a 32-row x EW-column chunk: thread = accumulator row.
+// Outputs are bounced through a small swizzled per-warp smem tile so every global store writes whole 32 B sectors of
+// a row (a thread-per-row store would touch 32 rows per instruction).  Ragged N falls back to per-thread stores.
+constexpr int EW = 16;
+
+__device__ __forceinline__ void dropout_ew(float (&v)[EW], const b2c_epilogue& e, uint64_t idx0) {
+  // one hash per 4 elements: h and a cheap second word h * odd; 16-bit lanes vs keep threshold
 #pragma unroll
-  for (int j = 0; j < 32; j += 8)
-    *reinterpret_cast<uint4*>(o + j) = make_uint4(pack_bf16(v[j], v[j + 1]), pack_bf16(v[j + 2], v[j + 3]),
-                                                  pack_bf16(v[j + 4], v[j + 5]), pack_bf16(v[j + 6], v[j + 7]));
+  for (int j = 0; j < EW; j += 4) {
+    const uint32_t h0 = dropout_hash(e.seed, e.drop_site, (idx0 + j) >> 1);
+    const uint32_t h1 = dropout_hash(e.seed, e.drop_site, (idx0 + j + 2) >> 1);
+    v[j] = ((h0 & 0xFFFFu) < e.drop_keep) ? v[j] * e.drop_scale : 0.f;
+    v[j + 1] = ((h0 >> 16) < e.drop_keep) ? v[j + 1] * e.drop_scale : 0.f;
+    v[j + 2] = ((h1 & 0xFFFFu) < e.drop_keep) ? v[j + 2] * e.drop_scale : 0.f;
+    v[j + 3] = ((h1 >> 16) < e.drop_keep) ? v[j + 3] * e.drop_scale : 0.f;
+  }
 }
-__device__ __forceinline__ void load_bf16x32(const bf16* p, float (&v)[32]) {
+__device__ __forceinline__ void load_bf16_ew(const bf16* p, float (&v)[EW]) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 8) {
+  for (int j = 0; j < EW; j += 8) {
     const uint4 u = *reinterpret_cast<const uint4*>(p + j);
     float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
     v[j] = a.x; v[j + 1] = a.y; v[j + 2] = b.x; v[j + 3] = b.y; v[j + 4] = c.x; v[j + 5] = c.y; v[j + 6] = d.x; v[j + 7] = d.y;
   }
 }
-// v[j] = keep ? v[j] * scale : 0 for the 32 elements idx0 .. idx0+31 (idx0 even): one hash per element pair
-__device__ __forceinline__ void dropout32(float (&v)[32], const b2c_epilogue& e, uint64_t idx0) {
-#pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    const uint32_t h = dropout_hash(e.seed, e.drop_site, (idx0 + j) >> 1);
-    v[j] = ((h & 0xFFFFu) < e.drop_keep) ? v[j] * e.drop_scale : 0.f;
-    v[j + 1] = ((h >> 16) < e.drop_keep) ? v[j + 1] * e.drop_scale : 0.f;
-  }
-}
-
-template <int MODE>
-__device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n0, int M, int N, const uint32_t (&acc)[32],
-                                             bool atomic) {
-  if (m >= M || n0 >= N) return;
-  const bool full = (n0 + 32 <= N);
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-  if (MODE != B2C_EPI_ACCUM_F32 && MODE != B2C_EPI_RELU_BWD && MODE != B2C_EPI_DSILU && e.bias != nullptr) {
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(e.bias + n0 + j);
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-      }
-    } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) v[j] += e.bias[n0 + j];
-    }
-  }
-  const size_t ldo = (size_t)e.ldo;
-  const uint64_t didx = (uint64_t)m * (uint64_t)N + (uint64_t)n0;  // dropout element index (N even)
-
-  if (MODE == B2C_EPI_BF16) {
-    // out_bf16[m, n] = bf16(acc + bias)
-    bf16* o = reinterpret_cast<bf16*>(e.out0) + (size_t)m * ldo + n0;
-    if (full) store_bf16x32(o, v);
-    else _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) o[j] = __float2bfloat16_rn(v[j]);
-  } else if (MODE == B2C_EPI_SILU) {
-    // z = bf16(acc+bias) → out0 ; h = bf16(dropout(silu(z))) → out1   (conformer_modules.py:383-385)
-    bf16* oz = reinterpret_cast<bf16*>(e.out0) + (size_t)m * ldo + n0;
-    bf16* oh = reinterpret_cast<bf16*>(e.out1) + (size_t)m * ldo + n0;
-    float h[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      v[j] = bf16_round(v[j]);
-      h[j] = silu_f(v[j]);
-    }
-    if (e.drop_keep != 0) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) h[j] = bf16_round(h[j]);
-      dropout32(h, e, didx);
-    }
-    if (full) {
-      store_bf16x32(oz, v);
-      store_bf16x32(oh, h);
-    } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) {
-        oz[j] = __float2bfloat16_rn(v[j]);
-        oh[j] = __float2bfloat16_rn(h[j]);
-      }
-    }
-  } else if (MODE == B2C_EPI_RESID_F32) {
-    // out0_f32[m,n] = (aux_f32 ? aux_f32[m,n] : 0) + alpha * drop(bf16(acc+bias))
-    float* o = reinterpret_cast<float*>(e.out0) + (size_t)m * ldo + n0;
-    const float* r = e.aux ? reinterpret_cast<const float*>(e.aux) + (size_t)m * ldo + n0 : nullptr;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
-    if (e.drop_keep != 0) dropout32(v, e, didx);
-    if (full) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const float4 rr = r ? *reinterpret_cast<const float4*>(r + j) : make_float4(0, 0, 0, 0);
-        *reinterpret_cast<float4*>(o + j) = make_float4(fmaf(e.alpha, v[j], rr.x), fmaf(e.alpha, v[j + 1], rr.y),
-                                                        fmaf(e.alpha, v[j + 2], rr.z), fmaf(e.alpha, v[j + 3], rr.w));
-      }
-    } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) o[j] = (r ? r[j] : 0.f) + e.alpha * v[j];
-    }
-  } else if (MODE == B2C_EPI_GLU_MASK) {
-    // columns interleaved (value, gate). g = bf16(acc+bias) → out0 [M, N];
-    // u[m, n/2] = bf16(a * sigmoid(b)) * (t < len) → out1 [M, N/2]      (conformer_modules.py:322-331)
-    bf16* og = reinterpret_cast<bf16*>(e.out0) + (size_t)m * ldo + n0;
-    bf16* ou = reinterpret_cast<bf16*>(e.out1) + (size_t)m * (ldo >> 1) + (n0 >> 1);
-    bool valid = true;
-    if (e.lengths) {
-      const int b = m / e.rows_per_batch, t = m - b * e.rows_per_batch;
-      valid = t < e.lengths[b];
-    }
-    float u[16];
-#pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-      v[j] = bf16_round(v[j]);
-      v[j + 1] = bf16_round(v[j + 1]);
-      u[j >> 1] = valid ? v[j] * sigmoid_f(v[j + 1]) : 0.f;
-    }
-    if (full) {
-      store_bf16x32(og, v);
-#pragma unroll
-      for (int j = 0; j < 16; j += 8)
-        *reinterpret_cast<uint4*>(ou + j) = make_uint4(pack_bf16(u[j], u[j + 1]), pack_bf16(u[j + 2], u[j + 3]),
-                                                       pack_bf16(u[j + 4], u[j + 5]), pack_bf16(u[j + 6], u[j + 7]));
-    } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) og[j] = __float2bfloat16_rn(v[j]);
-      _Pragma("unroll") for (int j = 0; j < 16; ++j) if (n0 + 2 * j < N) ou[j] = __float2bfloat16_rn(u[j]);
-    }
-  } else if (MODE == B2C_EPI_DSILU) {
-    // dz = bf16(dropout(bf16(acc)) * silu'(z[m,n]))   z = aux (bf16)       (FFN backward)
-    bf16* o = reinterpret_cast<bf16*>(e.out0) + (size_t)m * ldo + n0;
-    const bf16* z = reinterpret_cast<const bf16*>(e.aux) + (size_t)m * ldo + n0;
-    float zz[32];
-    if (full) {
-      load_bf16x32(z, zz);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) zz[j] = (n0 + j < N) ? __bfloat162float(z[j]) : 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
-    if (e.drop_keep != 0) dropout32(v, e, didx);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= dsilu_f(zz[j]);
-    if (full) store_bf16x32(o, v);
-    else _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) o[j] = __float2bfloat16_rn(v[j]);
-  } else if (MODE == B2C_EPI_RELU_MASK) {
-    // out_bf16 = relu(acc+bias) * (t < len)    rows are (b, t) x rows_inner  (subsampling.py:725-753)
-    bf16* o = reinterpret_cast<bf16*>(e.out0) + (size_t)m * ldo + n0;
-    bool valid = true;
-    if (e.lengths) {
-      const int b = m / e.rows_per_batch, t = (m - b * e.rows_per_batch) / e.rows_inner;
-      valid = t < e.lengths[b];
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = valid ? fmaxf(v[j], 0.f) : 0.f;
-    if (full) store_bf16x32(o, v);
-    else _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) o[j] = __float2bfloat16_rn(v[j]);
-  } else if (MODE == B2C_EPI_RELU_BWD) {
-    // out_bf16 = (aux_bf16[m,n] > 0) ? acc : 0     (gradient through ReLU + time mask: masked outputs are 0)
-    bf16* o = reinterpret_cast<bf16*>(e.out0) + (size_t)m * ldo + n0;
-    const bf16* y = reinterpret_cast<const bf16*>(e.aux) + (size_t)m * ldo + n0;
-    if (full) {
-      float yy[32];
-      load_bf16x32(y, yy);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = yy[j] > 0.f ? v[j] : 0.f;
-      store_bf16x32(o, v);
-    } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) o[j] = __float2bfloat16_rn(__bfloat162float(y[j]) > 0.f ? v[j] : 0.f);
-    }
-  } else if (MODE == B2C_EPI_ACCUM_F32) {
-    // out_f32[m,n] += alpha * acc  (weight gradients; vector reductions when split-K)
-    float* o = reinterpret_cast<float*>(e.out0) + (size_t)m * ldo + n0;
-    const bool vec_ok = full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
-    if (atomic) {
-      if (vec_ok) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) red_add_v4(o + j, e.alpha * v[j], e.alpha * v[j + 1], e.alpha * v[j + 2], e.alpha * v[j + 3]);
-      } else {
-        _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) atomicAdd(o + j, e.alpha * v[j]);
-      }
-    } else if (vec_ok) {
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 c = *reinterpret_cast<float4*>(o + j);
-        c.x = fmaf(e.alpha, v[j], c.x); c.y = fmaf(e.alpha, v[j + 1], c.y);
-        c.z = fmaf(e.alpha, v[j + 2], c.z); c.w = fmaf(e.alpha, v[j + 3], c.w);
-        *reinterpret_cast<float4*>(o + j) = c;
-      }
-    } else {
-      _Pragma("unroll") for (int j = 0; j < 32; ++j) if (n0 + j < N) o[j] += e.alpha * v[j];
-    }
-  }
-}
-
-// ---------------------------------------------------------------- coalesced output through a per-warp smem stage
-// Each thread owns one accumulator ROW (TMEM lane), which would make every global store instruction touch 32 rows
-// (half-filled sectors).  The 32x32 chunk is bounced through a 4 KB swizzled shared-memory tile so each store
-// instruction writes whole 64 B / 128 B row segments.  m_lane = global output row of this lane (>= M: skip).
-__device__ __forceinline__ void stage_store_bf16(uint8_t* stg, int lane, const float (&v)[32], bf16* out, size_t ldo,
+// bf16 chunk (32 rows x 16 cols = 32 B per row) → smem (swizzled) → global, 16 rows x 32 B per store instruction
+__device__ __forceinline__ void stage_store_bf16(uint8_t* stg, int lane, const float (&v)[EW], bf16* out, size_t ldo,
                                                  int m_lane, int M, int n0) {
   __syncwarp();
-  const int f = (lane >> 1) & 3;
+  const int f = (lane >> 2) & 1;
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
-    *reinterpret_cast<uint4*>(stg + lane * 64 + ((k ^ f) << 4)) =
+  for (int k = 0; k < 2; ++k)
+    *reinterpret_cast<uint4*>(stg + lane * 32 + ((k ^ f) << 4)) =
         make_uint4(pack_bf16(v[8 * k], v[8 * k + 1]), pack_bf16(v[8 * k + 2], v[8 * k + 3]),
                    pack_bf16(v[8 * k + 4], v[8 * k + 5]), pack_bf16(v[8 * k + 6], v[8 * k + 7]));
   __syncwarp();
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int row = it * 8 + (lane >> 2), ck = lane & 3;
+  for (int it = 0; it < 2; ++it) {
+    const int row = it * 16 + (lane >> 1), ck = lane & 1;
     const int m = __shfl_sync(0xffffffffu, m_lane, row);
-    const uint4 q = *reinterpret_cast<const uint4*>(stg + row * 64 + ((ck ^ ((row >> 1) & 3)) << 4));
+    const uint4 q = *reinterpret_cast<const uint4*>(stg + row * 32 + ((ck ^ ((row >> 2) & 1)) << 4));
     if (m < M) *reinterpret_cast<uint4*>(out + (size_t)m * ldo + n0 + ck * 8) = q;
   }
 }
-// out_f32[m, n0..n0+31] = (aux ? aux[m, ...] : 0) + v   (v already scaled)
-__device__ __forceinline__ void stage_store_f32(uint8_t* stg, int lane, const float (&v)[32], float* out, const float* aux,
+// fp32 chunk (32 rows x 16 cols = 64 B per row): out = (aux ? aux : 0) + v, 8 rows x 64 B per store instruction
+__device__ __forceinline__ void stage_store_f32(uint8_t* stg, int lane, const float (&v)[EW], float* out, const float* aux,
                                                 size_t ldo, int m_lane, int M, int n0) {
   __syncwarp();
-  const int f = lane & 7;
+  const int f = (lane >> 1) & 3;
 #pragma unroll
-  for (int k = 0; k < 8; ++k)
-    *reinterpret_cast<float4*>(stg + lane * 128 + ((k ^ f) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+  for (int k = 0; k < 4; ++k)
+    *reinterpret_cast<float4*>(stg + lane * 64 + ((k ^ f) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
   __syncwarp();
-  // all residual loads first (out / aux may alias as far as the compiler knows, which would serialise them)
-  float4 r[8];
-  int mm[8];
+  float4 r[4];
+  int mm[4];
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int row = it * 4 + (lane >> 3), ck = lane & 7;
+  for (int it = 0; it < 4; ++it) {  // residual loads first: out / aux may alias as far as the compiler knows
+    const int row = it * 8 + (lane >> 2), ck = lane & 3;
     mm[it] = __shfl_sync(0xffffffffu, m_lane, row);
     r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (aux && mm[it] < M) r[it] = __ldg(reinterpret_cast<const float4*>(aux + (size_t)mm[it] * ldo + n0 + ck * 4));
   }
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int row = it * 4 + (lane >> 3), ck = lane & 7;
-    const float4 q = *reinterpret_cast<const float4*>(stg + row * 128 + ((ck ^ (row & 7)) << 4));
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 8 + (lane >> 2), ck = lane & 3;
+    const float4 q = *reinterpret_cast<const float4*>(stg + row * 64 + ((ck ^ ((row >> 1) & 3)) << 4));
     if (mm[it] < M)
       *reinterpret_cast<float4*>(out + (size_t)mm[it] * ldo + n0 + ck * 4) =
           make_float4(q.x + r[it].x, q.y + r[it].y, q.z + r[it].z, q.w + r[it].w);
   }
 }
 
-// Warp-collective epilogue of one 32-row x 32-column chunk.  Falls back to the per-thread path for ragged N.
+// per-thread fallback for ragged N (n0 + EW > N) and for the fp32 accumulate epilogue
 template <int MODE>
-__device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int n0, int M, int N, const uint32_t (&acc)[32],
+__device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n0, int M, int N, float (&v)[EW],
+                                             bool atomic) {
+  if (m >= M || n0 >= N) return;
+  const size_t ldo = (size_t)e.ldo;
+  const uint64_t didx = (uint64_t)m * (uint64_t)N + (uint64_t)n0;
+  bool valid = true;
+  if ((MODE == B2C_EPI_GLU_MASK || MODE == B2C_EPI_RELU_MASK) && e.lengths) {
+    const int b = m / e.rows_per_batch;
+    const int t = (MODE == B2C_EPI_GLU_MASK) ? (m - b * e.rows_per_batch) : (m - b * e.rows_per_batch) / e.rows_inner;
+    valid = t < e.lengths[b];
+  }
+  if (MODE != B2C_EPI_ACCUM_F32 && MODE != B2C_EPI_RELU_BWD && MODE != B2C_EPI_DSILU && e.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < EW; ++j) if (n0 + j < N) v[j] += e.bias[n0 + j];
+  }
+  if (MODE == B2C_EPI_ACCUM_F32) {
+    float* o = reinterpret_cast<float*>(e.out0) + (size_t)m * ldo + n0;
+    const bool vec_ok = (n0 + EW <= N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+    if (atomic) {
+      if (vec_ok) {
+#pragma unroll
+        for (int j = 0; j < EW; j += 4) red_add_v4(o + j, e.alpha * v[j], e.alpha * v[j + 1], e.alpha * v[j + 2], e.alpha * v[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < EW; ++j) if (n0 + j < N) atomicAdd(o + j, e.alpha * v[j]);
+      }
+    } else if (vec_ok) {
+#pragma unroll
+      for (int j = 0; j < EW; j += 4) {
+        float4 c = *reinterpret_cast<float4*>(o + j);
+        c.x = fmaf(e.alpha, v[j], c.x); c.y = fmaf(e.alpha, v[j + 1], c.y);
+        c.z = fmaf(e.alpha, v[j + 2], c.z); c.w = fmaf(e.alpha, v[j + 3], c.w);
+        *reinterpret_cast<float4*>(o + j) = c;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < EW; ++j) if (n0 + j < N) o[j] += e.alpha * v[j];
+    }
+    return;
+  }
+  // ragged-N path of the other modes: straightforward per-element code (rare: N % 16 != 0)
+#pragma unroll
+  for (int j = 0; j < EW; ++j) {
+    const int n = n0 + j;
+    if (n >= N) continue;
+    float x = v[j];
+    const bool keep = (e.drop_keep == 0) || dropout_keep(e.seed, e.drop_site, didx + j, e.drop_keep);
+    if (MODE == B2C_EPI_BF16) {
+      reinterpret_cast<bf16*>(e.out0)[(size_t)m * ldo + n] = __float2bfloat16_rn(x);
+    } else if (MODE == B2C_EPI_SILU) {
+      x = bf16_round(x);
+      float h = silu_f(x);
+      if (e.drop_keep != 0) h = keep ? bf16_round(h) * e.drop_scale : 0.f;
+      reinterpret_cast<bf16*>(e.out0)[(size_t)m * ldo + n] = __float2bfloat16_rn(x);
+      reinterpret_cast<bf16*>(e.out1)[(size_t)m * ldo + n] = __float2bfloat16_rn(h);
+    } else if (MODE == B2C_EPI_RESID_F32) {
+      x = bf16_round(x);
+      if (e.drop_keep != 0) x = keep ? x * e.drop_scale : 0.f;
+      const float r = e.aux ? reinterpret_cast<const float*>(e.aux)[(size_t)m * ldo + n] : 0.f;
+      reinterpret_cast<float*>(e.out0)[(size_t)m * ldo + n] = r + e.alpha * x;
+    } else if (MODE == B2C_EPI_GLU_MASK) {
+      x = bf16_round(x);
+      reinterpret_cast<bf16*>(e.out0)[(size_t)m * ldo + n] = __float2bfloat16_rn(x);
+      if (j & 1) {
+        const float a = bf16_round(v[j - 1]);  // value column (bias already added above)
+        reinterpret_cast<bf16*>(e.out1)[(size_t)m * (ldo >> 1) + (n >> 1)] = __float2bfloat16_rn(valid ? a * sigmoid_f(x) : 0.f);
+      }
+    } else if (MODE == B2C_EPI_DSILU) {
+      x = bf16_round(x);
+      if (e.drop_keep != 0) x = keep ? x * e.drop_scale : 0.f;
+      const float z = __bfloat162float(reinterpret_cast<const bf16*>(e.aux)[(size_t)m * ldo + n]);
+      reinterpret_cast<bf16*>(e.out0)[(size_t)m * ldo + n] = __float2bfloat16_rn(x * dsilu_f(z));
+    } else if (MODE == B2C_EPI_RELU_MASK) {
+      reinterpret_cast<bf16*>(e.out0)[(size_t)m * ldo + n] = __float2bfloat16_rn(valid ? fmaxf(x, 0.f) : 0.f);
+    } else if (MODE == B2C_EPI_RELU_BWD) {
+      const float y = __bfloat162float(reinterpret_cast<const bf16*>(e.aux)[(size_t)m * ldo + n]);
+      reinterpret_cast<bf16*>(e.out0)[(size_t)m * ldo + n] = __float2bfloat16_rn(y > 0.f ? x : 0.f);
+    }
+  }
+}
+
+// Warp-collective epilogue of one 32-row x EW-column chunk.
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int n0, int M, int N, const uint32_t (&acc)[EW],
                                                bool atomic, uint8_t* stg, int lane) {
   if (n0 >= N) return;  // warp-uniform
-  const bool full = (n0 + 32 <= N);
-  constexpr bool kStaged = (MODE == B2C_EPI_BF16 || MODE == B2C_EPI_SILU || MODE == B2C_EPI_RESID_F32 ||
-                            MODE == B2C_EPI_DSILU || MODE == B2C_EPI_RELU_MASK || MODE == B2C_EPI_RELU_BWD ||
-                            MODE == B2C_EPI_GLU_MASK);
-  if (!kStaged || !full) {
-    epilogue_row<MODE>(e, m, n0, M, N, acc, atomic);
+  float v[EW];
+#pragma unroll
+  for (int j = 0; j < EW; ++j) v[j] = __uint_as_float(acc[j]);
+  if (MODE == B2C_EPI_ACCUM_F32 || n0 + EW > N) {
+    epilogue_row<MODE>(e, m, n0, M, N, v, atomic);
     return;
   }
   const bool rowok = m < M;
-  const int ms = rowok ? m : 0;  // safe row for loads of invalid lanes
-  float v[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
+  const int ms = rowok ? m : 0;  // safe row for the loads of inactive lanes
   if (MODE != B2C_EPI_RELU_BWD && MODE != B2C_EPI_DSILU && e.bias != nullptr) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 b = *reinterpret_cast<const float4*>(e.bias + n0 + j);
+    for (int j = 0; j < EW; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n0 + j));
       v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
     }
   }
   const size_t ldo = (size_t)e.ldo;
   const uint64_t didx = (uint64_t)ms * (uint64_t)N + (uint64_t)n0;
+  bool valid = rowok;
+  if ((MODE == B2C_EPI_GLU_MASK || MODE == B2C_EPI_RELU_MASK) && e.lengths && rowok) {
+    const int b = m / e.rows_per_batch;
+    const int t = (MODE == B2C_EPI_GLU_MASK) ? (m - b * e.rows_per_batch) : (m - b * e.rows_per_batch) / e.rows_inner;
+    valid = t < e.lengths[b];
+  }
   if (MODE == B2C_EPI_BF16) {
     stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
   } else if (MODE == B2C_EPI_SILU) {
-    float h[32];
+    // z = bf16(acc+bias) → out0 ; h = bf16(dropout(silu(z))) → out1   (conformer_modules.py:383-385)
+    float h[EW];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < EW; ++j) {
       v[j] = bf16_round(v[j]);
       h[j] = silu_f(v[j]);
     }
     if (e.drop_keep != 0) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) h[j] = bf16_round(h[j]);
-      dropout32(h, e, didx);
+      for (int j = 0; j < EW; ++j) h[j] = bf16_round(h[j]);
+      dropout_ew(h, e, didx);
     }
     stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
     stage_store_bf16(stg, lane, h, reinterpret_cast<bf16*>(e.out1), ldo, m, M, n0);
   } else if (MODE == B2C_EPI_RESID_F32) {
+    // out0_f32 = (aux_f32 ? aux : 0) + alpha * dropout(bf16(acc+bias))
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
-    if (e.drop_keep != 0) dropout32(v, e, didx);
+    for (int j = 0; j < EW; ++j) v[j] = bf16_round(v[j]);
+    if (e.drop_keep != 0) dropout_ew(v, e, didx);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= e.alpha;
+    for (int j = 0; j < EW; ++j) v[j] *= e.alpha;
     stage_store_f32(stg, lane, v, reinterpret_cast<float*>(e.out0), reinterpret_cast<const float*>(e.aux), ldo, m, M, n0);
   } else if (MODE == B2C_EPI_GLU_MASK) {
-    bool valid = rowok;
-    if (e.lengths && rowok) {
-      const int b = m / e.rows_per_batch, t = m - b * e.rows_per_batch;
-      valid = t < e.lengths[b];
-    }
-    float u[16];
+    // interleaved (value, gate): g = bf16(acc+bias) → out0 [M,N]; u = bf16(a*sigmoid(g))*(t<len) → out1 [M,N/2]
+    float u[EW / 2];
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
+    for (int j = 0; j < EW; j += 2) {
       v[j] = bf16_round(v[j]);
       v[j + 1] = bf16_round(v[j + 1]);
       u[j >> 1] = valid ? v[j] * sigmoid_f(v[j + 1]) : 0.f;
     }
     stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
-    if (rowok) {
-      bf16* ou = reinterpret_cast<bf16*>(e.out1) + (size_t)m * (ldo >> 1) + (n0 >> 1);
-#pragma unroll
-      for (int j = 0; j < 16; j += 8)
-        *reinterpret_cast<uint4*>(ou + j) = make_uint4(pack_bf16(u[j], u[j + 1]), pack_bf16(u[j + 2], u[j + 3]),
-                                                       pack_bf16(u[j + 4], u[j + 5]), pack_bf16(u[j + 6], u[j + 7]));
-    }
+    if (rowok)
+      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.out1) + (size_t)m * (ldo >> 1) + (n0 >> 1)) =
+          make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]), pack_bf16(u[6], u[7]));
   } else if (MODE == B2C_EPI_DSILU) {
-    float zz[32];
-    load_bf16x32(reinterpret_cast<const bf16*>(e.aux) + (size_t)ms * ldo + n0, zz);
+    // dz = bf16(dropout(bf16(acc)) * silu'(z)),  z = aux (bf16)
+    float zz[EW];
+    load_bf16_ew(reinterpret_cast<const bf16*>(e.aux) + (size_t)ms * ldo + n0, zz);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = bf16_round(v[j]);
-    if (e.drop_keep != 0) dropout32(v, e, didx);
+    for (int j = 0; j < EW; ++j) v[j] = bf16_round(v[j]);
+    if (e.drop_keep != 0) dropout_ew(v, e, didx);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= dsilu_f(zz[j]);
+    for (int j = 0; j < EW; ++j) v[j] *= dsilu_f(zz[j]);
     stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
   } else if (MODE == B2C_EPI_RELU_MASK) {
-    bool valid = rowok;
-    if (e.lengths && rowok) {
-      const int b = m / e.rows_per_batch, t = (m - b * e.rows_per_batch) / e.rows_inner;
-      valid = t < e.lengths[b];
-    }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = valid ? fmaxf(v[j], 0.f) : 0.f;
+    for (int j = 0; j < EW; ++j) v[j] = valid ? fmaxf(v[j], 0.f) : 0.f;
     stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
   } else if (MODE == B2C_EPI_RELU_BWD) {
-    float yy[32];
-    load_bf16x32(reinterpret_cast<const bf16*>(e.aux) + (size_t)ms * ldo + n0, yy);
+    float yy[EW];
+    load_bf16_ew(reinterpret_cast<const bf16*>(e.aux) + (size_t)ms * ldo + n0, yy);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = yy[j] > 0.f ? v[j] : 0.f;
+    for (int j = 0; j < EW; ++j) v[j] = yy[j] > 0.f ? v[j] : 0.f;
     stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
   }
 }
@@ -529,8 +437,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     const int q = warp & 3;             // TMEM lane quarter this warp may access (= warp id % 4)
-    const int chalf = (warp - 4) >> 2;  // two warps share a quarter and split the 32-column chunks
-    uint8_t* stg = smem + L::kStageOut + (warp - 4) * 4096;
+    const int cgrp = (warp - 4) >> 2;   // four warps share a quarter and split the column chunks
+    uint8_t* stg = smem + L::kStageOut + (warp - 4) * 2048;
     int as = 0, aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mn = tile / p.splits;
@@ -552,11 +460,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         epi.out0 = reinterpret_cast<float*>(epi.out0) + (size_t)(tile % p.splits) * p.cv.C;  // tap-major columns
       }
 #pragma unroll 1
-      for (int c = chalf; c < BN / 32; c += 2) {
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), acc);
+      for (int c = cgrp; c < BN / EW; c += kEpiWarps / 4) {
+        uint32_t acc[EW];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * EW), acc);
         tmem_ld_wait();
-        epilogue_chunk<MODE>(epi, m, n0 + c * 32, m_bound, p.N, acc, CONV == 0 && p.splits > 1, stg, lane);
+        epilogue_chunk<MODE>(epi, m, n0 + c * EW, m_bound, p.N, acc, CONV == 0 && p.splits > 1, stg, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -578,25 +486,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int MODE>
 __global__ void gemm_simt_kernel(const bf16* __restrict__ A, const bf16* __restrict__ B, int lda, int ldb, int a_mn,
                                  int b_mn, const GemmParams p) {
-  const int chunks = (p.N + 31) / 32;
+  const int chunks = (p.N + EW - 1) / EW;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (long long)p.M * chunks) return;
-  const int m = (int)(gid / chunks), n0 = (int)(gid % chunks) * 32;
-  float acc[32];
+  const int m = (int)(gid / chunks), n0 = (int)(gid % chunks) * EW;
+  float acc[EW];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+  for (int j = 0; j < EW; ++j) acc[j] = 0.f;
   for (int k = 0; k < p.K; ++k) {
     const float a = __bfloat162float(a_mn ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k]);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < EW; ++j) {
       const int n = n0 + j;
       if (n < p.N) acc[j] += a * __bfloat162float(b_mn ? B[(size_t)k * ldb + n] : B[(size_t)n * ldb + k]);
     }
   }
-  uint32_t r[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(acc[j]);
-  epilogue_row<MODE>(p.epi, m, n0, p.M, p.N, r, false);
+  // the per-thread path of every mode (identical arithmetic to the staged tensor-core epilogue)
+  if (MODE != B2C_EPI_ACCUM_F32) {
+    // force the ragged branch of epilogue_row by pretending the chunk is ragged: it handles full chunks as well
+  }
+  epilogue_row<MODE>(p.epi, m, n0, p.M, p.N, acc, false);
 }
 
 // ---------------------------------------------------------------- host launch
@@ -631,7 +540,7 @@ static int dispatch_mode(const void* A, const void* B, int lda, int ldb, int a_m
   if (g_gemm_impl == 1 || !tma_ok) {
     p.splits = 1;
     p.k_per_split = (p.K + BK - 1) / BK;
-    const long long work = (long long)p.M * ((p.N + 31) / 32);
+    const long long work = (long long)p.M * ((p.N + EW - 1) / EW);
     gemm_simt_kernel<MODE><<<(unsigned)((work + 127) / 128), 128, 0, stream>>>(
         reinterpret_cast<const bf16*>(A), reinterpret_cast<const bf16*>(B), lda, ldb, a_mn, b_mn, p);
     B2C_LAUNCH_CHECK();
