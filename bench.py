@@ -55,13 +55,16 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md) through NVML in a background thread
-    (the `nvidia-smi -lms` subprocess of the recipe measurably stalls kernel launches on this box; same counters)."""
+    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md) through NVML in a background thread.
+    NVML queries take a driver lock that stalls kernel submission (on some pool hosts a query costs ~100 ms: the
+    recipe's `nvidia-smi -lms 200`, or this thread at 5 Hz, tripled the step time), so the region is sampled sparsely:
+    once 0.15 s in, then every `period` seconds; the per-query cost is reported as `nvml_ms`."""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index=0, period=0.2):
+    def __init__(self, index=0, period=1.0):
         self.index, self.period, self.rows, self._stop, self.thr, self.err = index, period, [], False, None, None
+        self.cost = []
 
     def start(self):
         try:
@@ -74,17 +77,22 @@ class ClockSampler:
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
 
             def loop():
+                time.sleep(0.15)
                 while not self._stop:
                     try:
+                        t0 = time.perf_counter()
                         mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
                         try:
                             rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
                         except Exception:
                             rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                         self.rows.append((mhz, rs))
+                        self.cost.append((time.perf_counter() - t0) * 1e3)
                     except Exception as e:  # noqa: BLE001
                         self.err = repr(e)
-                    time.sleep(self.period)
+                    t_end = time.perf_counter() + self.period
+                    while not self._stop and time.perf_counter() < t_end:
+                        time.sleep(0.02)
 
             self.thr = threading.Thread(target=loop, daemon=True)
             self.thr.start()
@@ -104,7 +112,7 @@ class ClockSampler:
                 if rs & bit:
                     reasons.add(name)
         return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(self.max_mhz), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "nvml_ms": round(max(self.cost), 2) if self.cost else None}
 
 
 # ------------------------------------------------------------------------------------------------ reference / CPU arm
