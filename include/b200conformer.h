@@ -106,6 +106,12 @@ int b2c_permute3_bf16(const float* in, void* out_bf16, int A, int B, int C, int 
 int b2c_permute3_f32(const float* in, float* out, int A, int B, int C, int mode, int accumulate, void* stream);
 int b2c_fill_f32(float* p, long long n, float v, void* stream);
 
+/* CTC head (ConvASRDecoder.forward, nemo/collections/asr/modules/conv_asr.py:456-468): the 1x1 Conv1d is a b2c_gemm;
+ * these are the row log-softmax over the V classes of bf16 logits [M, ld] (ld >= V) → fp32 log-probs [M, V], and its
+ * backward dlogits = dlogp - exp(logp) * rowsum(dlogp) (bf16 [M, ld], pad columns zeroed). */
+int b2c_log_softmax_fwd(const void* logits_bf16, int ld, float* out, int M, int V, void* stream);
+int b2c_log_softmax_bwd(const float* dlogp, const float* logp, void* dlogits_bf16, int ld, int M, int V, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ conv module
  * Depthwise k-tap conv over time (symmetric pad (k-1)/2) + bias on channels-last [B*T, d] bf16 with per-channel
  * sum / sum-of-squares accumulation for BatchNorm (causal_convs.py:130-150, conformer_modules.py:332-342). */

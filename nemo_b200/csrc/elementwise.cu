@@ -273,6 +273,38 @@ __global__ void relpos_table_kernel(bf16* __restrict__ pe16, float* __restrict__
   }
 }
 
+
+// ---- CTC head (ConvASRDecoder, nemo/collections/asr/modules/conv_asr.py:456-468): row log-softmax of bf16 logits
+// one warp per row; logits [M, ld] bf16 (first V columns valid) → log-probs [M, V] fp32
+__global__ void __launch_bounds__(256)
+log_softmax_fwd_kernel(const bf16* __restrict__ logits, int ld, float* __restrict__ out, int M, int V) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const bf16* x = logits + (size_t)row * ld;
+  float mx = -3.0e38f;
+  for (int j = lane; j < V; j += 32) mx = fmaxf(mx, __bfloat162float(x[j]));
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int j = lane; j < V; j += 32) s += __expf(__bfloat162float(x[j]) - mx);
+  const float lse = mx + __logf(warp_sum(s));
+  float* o = out + (size_t)row * V;
+  for (int j = lane; j < V; j += 32) o[j] = __bfloat162float(x[j]) - lse;
+}
+// dlogits[m, j] = dlogp[m, j] - exp(logp[m, j]) * sum_j dlogp[m, j]   (bf16, pad columns [V, ld) zeroed)
+__global__ void __launch_bounds__(256)
+log_softmax_bwd_kernel(const float* __restrict__ dlogp, const float* __restrict__ logp, bf16* __restrict__ dlogits, int ld,
+                       int M, int V) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* g = dlogp + (size_t)row * V;
+  const float* lp = logp + (size_t)row * V;
+  float s = 0.f;
+  for (int j = lane; j < V; j += 32) s += g[j];
+  s = warp_sum(s);
+  bf16* o = dlogits + (size_t)row * ld;
+  for (int j = lane; j < ld; j += 32) o[j] = __float2bfloat16_rn(j < V ? g[j] - __expf(lp[j]) * s : 0.f);
+}
+
 // calc_length / calculate_conv_output_size with k=3, s=2, pad 1+1: L → (L + 2 - 3)//2 + 1 (floor), n times
 __global__ void subsample_lengths_kernel(const int64_t* __restrict__ len_in, int32_t* __restrict__ len_in32,
                                          int32_t* __restrict__ len_stage, int64_t* __restrict__ len_out64, int B,
@@ -417,6 +449,22 @@ extern "C" int b2c_subsample_lengths(const int64_t* len_in, int32_t* len_in32, i
   B2C_REQUIRE(B > 0 && n_convs >= 0, "subsample_lengths: bad args");
   subsample_lengths_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(len_in, len_in32, len_stage, len_out64, B,
                                                                              n_convs);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_log_softmax_fwd(const void* logits_bf16, int ld, float* out, int M, int V, void* stream) {
+  B2C_REQUIRE(M > 0 && V > 0 && ld >= V, "log_softmax_fwd: bad args");
+  log_softmax_fwd_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const bf16*>(logits_bf16), ld, out, M, V);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_log_softmax_bwd(const float* dlogp, const float* logp, void* dlogits_bf16, int ld, int M, int V,
+                                   void* stream) {
+  B2C_REQUIRE(M > 0 && V > 0 && ld >= V, "log_softmax_bwd: bad args");
+  log_softmax_bwd_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(dlogp, logp, reinterpret_cast<bf16*>(dlogits_bf16),
+                                                                         ld, M, V);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
 }
