@@ -62,7 +62,7 @@ class ClockSampler:
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index=0, period=1.0):
+    def __init__(self, index=0, period=0.4):
         self.index, self.period, self.rows, self._stop, self.thr, self.err = index, period, [], False, None, None
         self.cost = []
 
@@ -234,6 +234,8 @@ def run_ours(args):
         opt.step()
         return loss
 
+    per_step = []
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -247,13 +249,21 @@ def run_ours(args):
             E.L.gemm = timed_gemm
         launches0 = L.lib.b2c_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = []
         e0.record()
         for _ in range(n):
             loss = step(wav_host if from_host else wav_dev, len_host if from_host else len_dev, from_host)
             if from_host:
                 _ = loss.item()  # device→host read of the step's result
+            marks.append(torch.cuda.Event(enable_timing=True))
+            marks[-1].record()
         e1.record()
         barrier()
+        per_step.clear()
+        prev = e0
+        for mk in marks:
+            per_step.append(round(prev.elapsed_time(mk), 2))
+            prev = mk
         if profile_gemm:
             import nemo_b200.encoder as E
             L.gemm = orig_gemm
@@ -270,7 +280,9 @@ def run_ours(args):
         clocks.start()
     ms, launches = timed(args.steps, False)
     clk = clocks.stop() if rank == 0 else None
+    step_ms_value = list(per_step)
     ms_e2e, _ = timed(args.steps, True)
+    step_ms_e2e = list(per_step)
     # dominant-kernel roofline: every tcgen05 GEMM launch of one extra step bracketed by CUDA events
     gemm_events.clear()
     timed(1, False, profile_gemm=True)
@@ -292,6 +304,7 @@ def run_ours(args):
             "config": {"workload": f"Conformer-CTC-Large 18L d512 h8 k31 striding4x, {B}x30 s per GPU, mel+fwd+bwd+allreduce+AdamW",
                        "global_batch": world * B, "parallelism": f"dp{world}", "dropout": "0.1/0.1/att0.1",
                        "l2": "inputs+activations per step (>17 GB) exceed the 126 MB L2; no flush needed",
+                       "step_ms": step_ms_value, "step_ms_e2e": step_ms_e2e,
                        "model_tflop_per_step_per_gpu": step_flops / 1e12,
                        "model_tflops_achieved_per_gpu": step_flops / (ms / args.steps / 1e3) / 1e12},
             "e2e": {"value": e2e, "unit": "audio-sec/s", "h2d_bytes_per_step": world * (wav_host.numel() * 4 + B * 8),

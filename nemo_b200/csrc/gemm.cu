@@ -25,6 +25,7 @@ namespace b2c {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kEpiWarps = 16;
+constexpr int kCluster = 2;  // CTA pair (adjacent M tiles, same N tile): each CTA loads half of the B tile and multicasts it
 constexpr int kNumThreads = 128 + 32 * kEpiWarps;  // 4 role warps + 16 epilogue warps
 
 // Implicit-GEMM geometry of the 3x3 stride-2 subsampling convolution (no im2col is ever materialised: the
@@ -323,7 +324,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (CONV == 1 || CONV == 2) ? p.M : (p.M + BM - 1) / BM;  // conv fwd/dgrad: p.M = #row tiles
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int total_tiles = m_tiles * n_tiles * p.splits;
+  // Tiles are enumerated so that the two CTAs of a cluster (blockIdx.x = 2c, 2c+1; persistent stride is even) always
+  // work on M-adjacent tiles of the SAME n-tile / split at the same time: they share the B operand tile, each TMA-loads
+  // half of it and multicasts it to both.  An odd tile row count adds one dummy row tile (TMA zero-fills, epilogue skips).
+  const int m_pairs = (m_tiles + kCluster - 1) / kCluster;
+  const int total_tiles = m_pairs * kCluster * n_tiles * p.splits;
+  const uint32_t crank = (kCluster > 1) ? cluster_ctarank() : 0u;
+  auto decode = [&](int tile, int& m_blk, int& n_blk, int& split) {
+    const int pair = tile / kCluster;
+    split = pair % p.splits;
+    const int mn2 = pair / p.splits;
+    n_blk = mn2 % n_tiles;
+    m_blk = (mn2 / n_tiles) * kCluster + (tile % kCluster);
+  };
   const int kb_total = (CONV != 0) ? p.K : (p.K + BK - 1) / BK;               // conv: p.K = #k-blocks
   // bytes one stage receives (partial boxes of the conv gathers deliver fewer rows than the slot holds)
   const uint32_t stage_tx = (CONV == 1 || CONV == 2) ? (uint32_t)(p.cv.TR * p.cv.Fq * BK * 2 + L::kBBytes)
@@ -343,7 +356,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], kCluster);  // a stage is reusable once BOTH CTAs' MMAs have consumed it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -354,16 +367,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();  // peer barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0, phase = 0;
+      constexpr uint16_t kMask = (uint16_t)((1u << kCluster) - 1);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int split = tile % p.splits;
-        const int mn = tile / p.splits;
-        const int m0 = (mn / n_tiles) * BM, n0 = (mn % n_tiles) * BN;
+        int m_blk, n_blk, split;
+        decode(tile, m_blk, n_blk, split);
+        const int m0 = m_blk * BM, n0 = n_blk * BN;
         const int kb0 = (CONV == 3) ? 0 : split * p.k_per_split;
         const int kb1 = (CONV == 3) ? kb_total : min(kb_total, kb0 + p.k_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -371,34 +386,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
           mbar_expect_tx(&full_bar[stage], stage_tx);
+          // ---- A operand: private to this CTA
           if (CONV == 1 || CONV == 2) {
             const int cblks = p.cv.C / BK;
             const int tap = kb / cblks, c0 = (kb - tap * cblks) * BK;
-            const int mb = mn / n_tiles;
-            const int bb = mb / p.cv.tiles_per_batch, t0 = (mb - bb * p.cv.tiles_per_batch) * p.cv.TR;
+            const int bb = m_blk / p.cv.tiles_per_batch, t0 = (m_blk - bb * p.cv.tiles_per_batch) * p.cv.TR;
             tma_load_4d(sa, &tmA, &full_bar[stage], c0, p.cv.tap_f[tap], t0 * p.cv.a_t_mul + p.cv.tap_t[tap], bb);
-            tma_load_2d(sb, &tmB, &full_bar[stage], p.cv.tap_k[tap] + c0, n0);
           } else if (CONV == 3) {
             const int bb = kb / p.cv.tiles_per_batch, t0 = (kb - bb * p.cv.tiles_per_batch) * p.cv.TR;
-            const int tap = split;  // kh*3 + kw
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c) tma_load_4d(sa + c * (64 * BK * 2), &tmA, &full_bar[stage], m0 + c * 64, 0, t0, bb);
-#pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_4d(sb + c * (64 * BK * 2), &tmB, &full_bar[stage], n0 + c * 64, tap % 3 - 1, 2 * t0 + tap / 3 - 1, bb);
-          } else
-          if (A_MN) {
+          } else if (A_MN) {
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (64 * BK * 2), &tmA, &full_bar[stage], m0 + c * 64, kb * BK);
           } else {
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
           }
-          if (CONV != 0) {
+          // ---- B operand: this CTA fetches its 1/kCluster share and multicasts it to the whole cluster
+          if (CONV == 3) {
+            const int bb = kb / p.cv.tiles_per_batch, t0 = (kb - bb * p.cv.tiles_per_batch) * p.cv.TR;
+            const int tap = split;  // kh*3 + kw
+#pragma unroll
+            for (int c = 0; c < BN / 64 / kCluster; ++c) {
+              const int cc = (int)crank * (BN / 64 / kCluster) + c;
+              tma_load_4d_mc(sb + cc * (64 * BK * 2), &tmB, &full_bar[stage], n0 + cc * 64, tap % 3 - 1, 2 * t0 + tap / 3 - 1, bb, kMask);
+            }
+          } else if (CONV == 1 || CONV == 2) {
+            const int cblks = p.cv.C / BK;
+            const int tap = kb / cblks, c0 = (kb - tap * cblks) * BK;
+            tma_load_2d_mc(sb + crank * (BN / kCluster) * (BK * 2), &tmB, &full_bar[stage], p.cv.tap_k[tap] + c0,
+                           n0 + (int)crank * (BN / kCluster), kMask);
           } else if (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (64 * BK * 2), &tmB, &full_bar[stage], n0 + c * 64, kb * BK);
+            for (int c = 0; c < BN / 64 / kCluster; ++c) {
+              const int cc = (int)crank * (BN / 64 / kCluster) + c;
+              tma_load_2d_mc(sb + cc * (64 * BK * 2), &tmB, &full_bar[stage], n0 + cc * 64, kb * BK, kMask);
+            }
           } else {
-            tma_load_2d(sb, &tmB, &full_bar[stage], kb * BK, n0);
+            tma_load_2d_mc(sb + crank * (BN / kCluster) * (BK * 2), &tmB, &full_bar[stage], kb * BK,
+                           n0 + (int)crank * (BN / kCluster), kMask);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -409,7 +435,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
       int stage = 0, phase = 0, as = 0, aphase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int split = tile % p.splits;
+        int m_blk, n_blk, split;
+        decode(tile, m_blk, n_blk, split);
         const int kb0 = (CONV == 3) ? 0 : split * p.k_per_split;
         const int kb1 = (CONV == 3) ? kb_total : min(kb_total, kb0 + p.k_per_split);
         mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -428,7 +455,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t db = B_MN ? umma_desc_sw128(sb + k * 2048, 64 * BK * 2, 1024) : umma_desc_sw128(sb + k * 32, 16, 1024);
             umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot once these MMAs retire — in BOTH CTAs: the peer multicasts into this slot too
+          if (kCluster > 1) umma_commit_mc(&empty_bar[stage], (uint16_t)((1u << kCluster) - 1));
+          else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[as]);  // accumulator complete → epilogue
@@ -441,23 +470,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* stg = smem + L::kStageOut + (warp - 4) * 2048;
     int as = 0, aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mn = tile / p.splits;
-      const int m0 = (mn / n_tiles) * BM, n0 = (mn % n_tiles) * BN;
+      int m_blk, n_blk, split;
+      decode(tile, m_blk, n_blk, split);
+      const int m0 = m_blk * BM, n0 = n_blk * BN;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       int m = m0 + q * 32 + lane, m_bound = p.M;
       b2c_epilogue epi = p.epi;
       if (CONV == 1 || CONV == 2) {
-        const int mb = mn / n_tiles;
+        const int mb = m_blk;
         const int bb = mb / p.cv.tiles_per_batch, t0 = (mb - bb * p.cv.tiles_per_batch) * p.cv.TR;
         const int r = q * 32 + lane;
         const int tl = r / p.cv.Fq, fl = r - tl * p.cv.Fq, t = t0 + tl;
         m_bound = 0x7fffffff;
-        m = (r < p.cv.TR * p.cv.Fq && t < p.cv.Tq)
+        m = (mb < m_tiles && r < p.cv.TR * p.cv.Fq && t < p.cv.Tq)
                 ? ((bb * p.cv.To + t * p.cv.ts + p.cv.pt) * p.cv.Fo + fl * p.cv.fs + p.cv.pf)
                 : m_bound;
       } else if (CONV == 3) {
-        epi.out0 = reinterpret_cast<float*>(epi.out0) + (size_t)(tile % p.splits) * p.cv.C;  // tap-major columns
+        epi.out0 = reinterpret_cast<float*>(epi.out0) + (size_t)split * p.cv.C;  // tap-major columns
       }
 #pragma unroll 1
       for (int c = cgrp; c < BN / EW; c += kEpiWarps / 4) {
@@ -474,6 +504,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) cluster_sync_all();  // no CTA may exit while its peer can still multicast into / arrive on its smem
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<2 * BN>(tmem_base);
@@ -521,10 +552,23 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
     attr_set = true;
   }
   const int m_tiles = (CONV == 1 || CONV == 2) ? p.M : (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
-  const int total = m_tiles * n_tiles * p.splits;
-  const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, kNumThreads, L::kTotal, stream>>>(ta, tb, p);
-  B2C_LAUNCH_CHECK();
+  const int total = ((m_tiles + kCluster - 1) / kCluster) * kCluster * n_tiles * p.splits;
+  int grid = total < num_sms() ? total : num_sms();
+  grid -= grid % kCluster;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  count_launch();
+  B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
   return B2C_OK;
 }
 
@@ -563,7 +607,7 @@ static int dispatch_mode(const void* A, const void* B, int lda, int ldb, int a_m
   }
   CUtensorMap ta, tb;
   {
-    // K-major: dims {K, rows}, box {64, 128|BN};  MN-major: dims {rows, K}, box {64, 64}
+    // K-major: dims {K, rows}, box {64, 128 (A) | BN/kCluster (B)};  MN-major: dims {rows, K}, box {64, 64}
     uint64_t dims[2], strides[1];
     uint32_t box[2], es[2] = {1, 1};
     if (a_mn) { dims[0] = p.M; dims[1] = p.K; box[0] = 64; box[1] = BK; }
@@ -572,7 +616,7 @@ static int dispatch_mode(const void* A, const void* B, int lda, int ldb, int a_m
     int rc = make_tmap(&ta, A, 2, 2, dims, strides, box, es, 1);
     if (rc) return rc;
     if (b_mn) { dims[0] = p.N; dims[1] = p.K; box[0] = 64; box[1] = BK; }
-    else      { dims[0] = p.K; dims[1] = p.N; box[0] = BK; box[1] = BN; }
+    else      { dims[0] = p.K; dims[1] = p.N; box[0] = BK; box[1] = BN / kCluster; }  // each CTA of the pair loads its share
     strides[0] = (uint64_t)ldb * 2;
     rc = make_tmap(&tb, B, 2, 2, dims, strides, box, es, 1);
     if (rc) return rc;
@@ -642,7 +686,7 @@ int conv3x3s2_fwd(const void* in, const void* w_bf16, const float* bias, const i
   int rc = conv_map4d(&ta, in, C, F1, T1, B, 64, F2, g.TR, 2);
   if (rc) return rc;
   uint64_t dims[2] = {(uint64_t)9 * C, (uint64_t)C}, strides[1] = {(uint64_t)9 * C * 2};
-  uint32_t box[2] = {(uint32_t)BK, (uint32_t)(wide ? 256 : 128)}, es[2] = {1, 1};
+  uint32_t box[2] = {(uint32_t)BK, (uint32_t)((wide ? 256 : 128) / kCluster)}, es[2] = {1, 1};
   rc = make_tmap(&tb, w_bf16, 2, 2, dims, strides, box, es, 1);
   if (rc) return rc;
   if (wide) return launch_tc<256, 0, 0, B2C_EPI_RELU_MASK, 1>(ta, tb, p, stream);
@@ -659,7 +703,7 @@ int conv3x3s2_bwd_data(const void* dy, const void* wd_bf16, const void* x, void*
   CUtensorMap tb;
   {
     uint64_t dims[2] = {(uint64_t)9 * C, (uint64_t)C}, strides[1] = {(uint64_t)9 * C * 2};
-    uint32_t box[2] = {(uint32_t)BK, (uint32_t)(wide ? 256 : 128)}, es[2] = {1, 1};
+    uint32_t box[2] = {(uint32_t)BK, (uint32_t)((wide ? 256 : 128) / kCluster)}, es[2] = {1, 1};
     int rc = make_tmap(&tb, wd_bf16, 2, 2, dims, strides, box, es, 1);
     if (rc) return rc;
   }
