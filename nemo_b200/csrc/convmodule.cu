@@ -50,18 +50,32 @@ dwconv_fwd_kernel(const bf16* __restrict__ u, const float* __restrict__ w, const
     __syncthreads();
     if (act) {
       const int nt = min(kTT, T - t0);
-      for (int i = 0; i < nt; ++i) {
-        float a0 = b0, a1 = b1;
+      // register blocking: 4 consecutive outputs share every staged input row (each row is read / unpacked once)
+      for (int i = 0; i < nt; i += 4) {
+        float a0[4], a1[4];
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-          const float2 x = unpack_bf16(su[(i + j) * 128 + threadIdx.x]);
-          a0 = fmaf(w0[j], x.x, a0);
-          a1 = fmaf(w1[j], x.y, a1);
+        for (int o = 0; o < 4; ++o) { a0[o] = b0; a1[o] = b1; }
+#pragma unroll
+        for (int r = 0; r < K + 3; ++r) {
+          const float2 x = unpack_bf16(su[(i + r) * 128 + threadIdx.x]);
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            const int j = r - o;
+            if (j >= 0 && j < K) {
+              a0[o] = fmaf(w0[j], x.x, a0[o]);
+              a1[o] = fmaf(w1[j], x.y, a1[o]);
+            }
+          }
         }
-        const uint32_t packed = pack_bf16(a0, a1);
-        *reinterpret_cast<uint32_t*>(cb + (size_t)(t0 + i) * d + ch) = packed;
-        const float2 r = unpack_bf16(packed);  // BatchNorm sees the bf16 conv output
-        s0 += r.x; s1 += r.y; q0 += r.x * r.x; q1 += r.y * r.y;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          if (i + o < nt) {
+            const uint32_t packed = pack_bf16(a0[o], a1[o]);
+            *reinterpret_cast<uint32_t*>(cb + (size_t)(t0 + i + o) * d + ch) = packed;
+            const float2 r2 = unpack_bf16(packed);  // BatchNorm sees the bf16 conv output
+            s0 += r2.x; s1 += r2.y; q0 += r2.x * r2.x; q1 += r2.y * r2.y;
+          }
+        }
       }
     }
   }
@@ -218,25 +232,45 @@ dwconv_bwd_kernel(const bf16* __restrict__ dc, const bf16* __restrict__ u, const
     __syncthreads();
     if (act) {
       const int nt = min(kTT, T - t0);
-      for (int i = 0; i < nt; ++i) {
-        // du[t0+i]: dc index (t0+i) + PAD - j  ↔ smem row i + 2*PAD - j
-        float a0 = 0.f, a1 = 0.f;
+      for (int i = 0; i < nt; i += 4) {
+        // ---- du[t0+i+o] = sum_j w[j] * dc[(t0+i+o) + PAD - j]  ↔ smem row (i + o + 2*PAD - j); 4 outputs per row pass
+        float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-          const float2 x = unpack_bf16(sdc[(i + 2 * PAD - j) * 128 + threadIdx.x]);
-          a0 = fmaf(w0[j], x.x, a0);
-          a1 = fmaf(w1[j], x.y, a1);
+        for (int r = 0; r < K + 3; ++r) {  // r = smem row - i
+          const float2 x = unpack_bf16(sdc[(i + r) * 128 + threadIdx.x]);
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            const int j = o + 2 * PAD - r;
+            if (j >= 0 && j < K) {
+              a0[o] = fmaf(w0[j], x.x, a0[o]);
+              a1[o] = fmaf(w1[j], x.y, a1[o]);
+            }
+          }
         }
-        const bool valid = (t0 + i) < len;
-        *reinterpret_cast<uint32_t*>(dub + (size_t)(t0 + i) * d + ch) = valid ? pack_bf16(a0, a1) : 0u;
-        // dw: dc[t0+i] (smem row i+PAD) times u[t0+i+j-PAD] (smem row i+j)
-        const float2 g = unpack_bf16(sdc[(i + PAD) * 128 + threadIdx.x]);
-        db0 += g.x; db1 += g.y;
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-          const float2 x = unpack_bf16(suu[(i + j) * 128 + threadIdx.x]);
-          g0[j] = fmaf(g.x, x.x, g0[j]);
-          g1[j] = fmaf(g.y, x.y, g1[j]);
+        for (int o = 0; o < 4; ++o)
+          if (i + o < nt) {
+            const bool valid = (t0 + i + o) < len;
+            *reinterpret_cast<uint32_t*>(dub + (size_t)(t0 + i + o) * d + ch) = valid ? pack_bf16(a0[o], a1[o]) : 0u;
+          }
+        // ---- dw[j] += dc[t0+i+o] (smem row i+o+PAD) * u[t0+i+o+j-PAD] (smem row i+o+j); db += dc
+        float2 g[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          g[o] = (i + o < nt) ? unpack_bf16(sdc[(i + o + PAD) * 128 + threadIdx.x]) : make_float2(0.f, 0.f);
+          db0 += g[o].x; db1 += g[o].y;
+        }
+#pragma unroll
+        for (int r = 0; r < K + 3; ++r) {  // u smem row i + r feeds tap j = r - o of output o
+          const float2 x = unpack_bf16(suu[(i + r) * 128 + threadIdx.x]);
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            const int j = r - o;
+            if (j >= 0 && j < K) {
+              g0[j] = fmaf(g[o].x, x.x, g0[j]);
+              g1[j] = fmaf(g[o].y, x.y, g1[j]);
+            }
+          }
         }
       }
     }

@@ -65,7 +65,7 @@ struct DropArgs {
 
 // rows handled per warp are strided so each warp keeps per-column dgamma/dbeta partials in registers
 template <bool DY_BF16, int kMaxVec>
-__global__ void __launch_bounds__(256, (kMaxVec <= 4) ? 3 : 2)
+__global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dr,
                      int accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta, bf16* __restrict__ next16,
@@ -78,34 +78,33 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, 
   float4 ag[kMaxVec], ab[kMaxVec];
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i) ag[i] = ab[i] = make_float4(0, 0, 0, 0);
+  auto load_dy = [&](int row, int c) -> float4 {
+    if (DY_BF16) {
+      const uint2 u = reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy_) + (size_t)row * d)[c];
+      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+      return make_float4(a.x, a.y, b.x, b.y);
+    }
+    return reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (size_t)row * d)[c];
+  };
   for (int row = blockIdx.x * wpb + wib; row < M; row += gridDim.x * wpb) {
     const float mu = mean[row], rs = rstd[row];
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d);
-    float4 xh[kMaxVec], dyv[kMaxVec];
+    // pass 1: row sums for dx and the dgamma / dbeta partials (nothing is kept in registers across the reduction;
+    // pass 2 re-reads x / dy from L1 — fewer live registers → more resident warps → more bytes in flight)
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) {
       const int c = i * 32 + lane;
       if (c < nv) {
-        float4 xv = xr[c];
-        float4 dv;
-        if (DY_BF16) {
-          uint2 u = reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy_) + (size_t)row * d)[c];
-          float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
-          dv = make_float4(a.x, a.y, b.x, b.y);
-        } else {
-          dv = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (size_t)row * d)[c];
-        }
-        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        dyv[i] = dv;
-        ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
-        ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
+        const float4 xv = xr[c];
+        const float4 dv = load_dy(row, c);
         const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        const float4 xh = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        ag[i].x += dv.x * xh.x; ag[i].y += dv.y * xh.y; ag[i].z += dv.z * xh.z; ag[i].w += dv.w * xh.w;
+        ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
         const float a0 = dv.x * gm.x, a1 = dv.y * gm.y, a2 = dv.z * gm.z, a3 = dv.w * gm.w;
         s1 += a0 + a1 + a2 + a3;
-        s2 += a0 * xh[i].x + a1 * xh[i].y + a2 * xh[i].z + a3 * xh[i].w;
-      } else {
-        xh[i] = dyv[i] = make_float4(0, 0, 0, 0);
+        s2 += a0 * xh.x + a1 * xh.y + a2 * xh.z + a3 * xh.w;
       }
     }
     s1 = warp_sum(s1) / (float)d;
@@ -114,15 +113,17 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, 
     for (int i = 0; i < kMaxVec; ++i) {
       const int c = i * 32 + lane;
       if (c < nv) {
+        const float4 xv = xr[c];
+        const float4 dv = load_dy(row, c);
         const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
         float4 o;
-        o.x = rs * (dyv[i].x * gm.x - s1 - xh[i].x * s2);
-        o.y = rs * (dyv[i].y * gm.y - s1 - xh[i].y * s2);
-        o.z = rs * (dyv[i].z * gm.z - s1 - xh[i].z * s2);
-        o.w = rs * (dyv[i].w * gm.w - s1 - xh[i].w * s2);
+        o.x = rs * (dv.x * gm.x - s1 - (xv.x - mu) * rs * s2);
+        o.y = rs * (dv.y * gm.y - s1 - (xv.y - mu) * rs * s2);
+        o.z = rs * (dv.z * gm.z - s1 - (xv.z - mu) * rs * s2);
+        o.w = rs * (dv.w * gm.w - s1 - (xv.w - mu) * rs * s2);
         float4* drp = reinterpret_cast<float4*>(dr + (size_t)row * d) + c;
         if (accumulate) {
-          float4 p = *drp;
+          const float4 p = *drp;
           o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
         }
         *drp = o;
@@ -130,10 +131,11 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, 
           float n0 = o.x * next_scale, n1 = o.y * next_scale, n2 = o.z * next_scale, n3 = o.w * next_scale;
           if (drop.keep != 0) {
             const uint64_t idx = (uint64_t)row * (uint64_t)d + (uint64_t)c * 4;
-            n0 = dropout_keep(drop.seed, drop.site, idx, drop.keep) ? n0 * drop.scale : 0.f;
-            n1 = dropout_keep(drop.seed, drop.site, idx + 1, drop.keep) ? n1 * drop.scale : 0.f;
-            n2 = dropout_keep(drop.seed, drop.site, idx + 2, drop.keep) ? n2 * drop.scale : 0.f;
-            n3 = dropout_keep(drop.seed, drop.site, idx + 3, drop.keep) ? n3 * drop.scale : 0.f;
+            const uint32_t h0 = dropout_hash(drop.seed, drop.site, idx >> 1), h1 = dropout_hash(drop.seed, drop.site, (idx + 2) >> 1);
+            n0 = ((h0 & 0xFFFFu) < drop.keep) ? n0 * drop.scale : 0.f;
+            n1 = ((h0 >> 16) < drop.keep) ? n1 * drop.scale : 0.f;
+            n2 = ((h1 & 0xFFFFu) < drop.keep) ? n2 * drop.scale : 0.f;
+            n3 = ((h1 >> 16) < drop.keep) ? n3 * drop.scale : 0.f;
           }
           reinterpret_cast<uint2*>(next16 + (size_t)row * d)[c] = make_uint2(pack_bf16(n0, n1), pack_bf16(n2, n3));
         }
@@ -354,7 +356,7 @@ extern "C" int b2c_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x,
   }
   const int wpb = 8;
   int grid = (M + wpb - 1) / wpb;
-  const int cap = num_sms() * 4;
+  const int cap = num_sms() * (d <= 512 ? 3 : 2);  // = resident CTAs: one wave, rows strided across it
   if (grid > cap) grid = cap;
   const size_t smem = 2 * (size_t)d * sizeof(float);
   bf16* nx = reinterpret_cast<bf16*>(next_bf16);
