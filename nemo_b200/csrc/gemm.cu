@@ -104,31 +104,36 @@ __device__ __forceinline__ void stage_store_bf16(uint8_t* stg, int lane, const f
     if (m < M) *reinterpret_cast<uint4*>(out + (size_t)m * ldo + n0 + ck * 8) = q;
   }
 }
-// fp32 chunk (32 rows x 16 cols = 64 B per row): out = (aux ? aux : 0) + v, 8 rows x 64 B per store instruction
-__device__ __forceinline__ void stage_store_f32(uint8_t* stg, int lane, const float (&v)[EW], float* out, const float* aux,
-                                                size_t ldo, int m_lane, int M, int n0) {
+// fp32 chunk (32 rows x 16 cols = 64 B per row): out = residual + v, 8 rows x 64 B per store instruction.
+// The residual (aux) tile is fetched by resid_prefetch() BEFORE the epilogue maths so its latency is hidden.
+struct ResidTile {
+  float4 r[4];
+  int mm[4];
+};
+__device__ __forceinline__ void resid_prefetch(ResidTile& t, const float* aux, size_t ldo, int m_lane, int M, int n0, int lane) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int row = it * 8 + (lane >> 2), ck = lane & 3;
+    t.mm[it] = __shfl_sync(0xffffffffu, m_lane, row);
+    t.r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (aux && t.mm[it] < M) t.r[it] = __ldg(reinterpret_cast<const float4*>(aux + (size_t)t.mm[it] * ldo + n0 + ck * 4));
+  }
+}
+__device__ __forceinline__ void stage_store_f32(uint8_t* stg, int lane, const float (&v)[EW], float* out, const ResidTile& t,
+                                                size_t ldo, int M, int n0) {
   __syncwarp();
   const int f = (lane >> 1) & 3;
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     *reinterpret_cast<float4*>(stg + lane * 64 + ((k ^ f) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
   __syncwarp();
-  float4 r[4];
-  int mm[4];
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {  // residual loads first: out / aux may alias as far as the compiler knows
-    const int row = it * 8 + (lane >> 2), ck = lane & 3;
-    mm[it] = __shfl_sync(0xffffffffu, m_lane, row);
-    r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (aux && mm[it] < M) r[it] = __ldg(reinterpret_cast<const float4*>(aux + (size_t)mm[it] * ldo + n0 + ck * 4));
-  }
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int row = it * 8 + (lane >> 2), ck = lane & 3;
     const float4 q = *reinterpret_cast<const float4*>(stg + row * 64 + ((ck ^ ((row >> 1) & 3)) << 4));
-    if (mm[it] < M)
-      *reinterpret_cast<float4*>(out + (size_t)mm[it] * ldo + n0 + ck * 4) =
-          make_float4(q.x + r[it].x, q.y + r[it].y, q.z + r[it].z, q.w + r[it].w);
+    if (t.mm[it] < M)
+      *reinterpret_cast<float4*>(out + (size_t)t.mm[it] * ldo + n0 + ck * 4) =
+          make_float4(q.x + t.r[it].x, q.y + t.r[it].y, q.z + t.r[it].z, q.w + t.r[it].w);
   }
 }
 
@@ -216,9 +221,31 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
 }
 
 // Warp-collective epilogue of one 32-row x EW-column chunk.
+// bf16 side input (z for SiLU', y for ReLU') of one row chunk, fetched one chunk ahead of its use
+struct AuxChunk {
+  uint4 q[2];
+};
+template <int MODE>
+__device__ __forceinline__ void aux_prefetch(AuxChunk& a, const b2c_epilogue& e, int m, int n0, int M, int N) {
+  a.q[0] = a.q[1] = make_uint4(0, 0, 0, 0);
+  if ((MODE == B2C_EPI_DSILU || MODE == B2C_EPI_RELU_BWD) && m < M && n0 + EW <= N) {
+    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(e.aux) + (size_t)m * (size_t)e.ldo + n0);
+    a.q[0] = __ldg(p);
+    a.q[1] = __ldg(p + 1);
+  }
+}
+__device__ __forceinline__ void unpack_aux(const AuxChunk& a, float (&v)[EW]) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const float2 x0 = unpack_bf16(a.q[h].x), x1 = unpack_bf16(a.q[h].y), x2 = unpack_bf16(a.q[h].z), x3 = unpack_bf16(a.q[h].w);
+    v[8 * h] = x0.x; v[8 * h + 1] = x0.y; v[8 * h + 2] = x1.x; v[8 * h + 3] = x1.y;
+    v[8 * h + 4] = x2.x; v[8 * h + 5] = x2.y; v[8 * h + 6] = x3.x; v[8 * h + 7] = x3.y;
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int n0, int M, int N, const uint32_t (&acc)[EW],
-                                               bool atomic, uint8_t* stg, int lane) {
+                                               const AuxChunk& auxc, bool atomic, uint8_t* stg, int lane) {
   if (n0 >= N) return;  // warp-uniform
   float v[EW];
 #pragma unroll
@@ -229,6 +256,8 @@ __device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int
   }
   const bool rowok = m < M;
   const int ms = rowok ? m : 0;  // safe row for the loads of inactive lanes
+  ResidTile rt;
+  if (MODE == B2C_EPI_RESID_F32) resid_prefetch(rt, reinterpret_cast<const float*>(e.aux), (size_t)e.ldo, m, M, n0, lane);
   if (MODE != B2C_EPI_RELU_BWD && MODE != B2C_EPI_DSILU && e.bias != nullptr) {
 #pragma unroll
     for (int j = 0; j < EW; j += 4) {
@@ -268,7 +297,7 @@ __device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int
     if (e.drop_keep != 0) dropout_ew(v, e, didx);
 #pragma unroll
     for (int j = 0; j < EW; ++j) v[j] *= e.alpha;
-    stage_store_f32(stg, lane, v, reinterpret_cast<float*>(e.out0), reinterpret_cast<const float*>(e.aux), ldo, m, M, n0);
+    stage_store_f32(stg, lane, v, reinterpret_cast<float*>(e.out0), rt, ldo, M, n0);
   } else if (MODE == B2C_EPI_GLU_MASK) {
     // interleaved (value, gate): g = bf16(acc+bias) → out0 [M,N]; u = bf16(a*sigmoid(g))*(t<len) → out1 [M,N/2]
     float u[EW / 2];
@@ -285,7 +314,7 @@ __device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int
   } else if (MODE == B2C_EPI_DSILU) {
     // dz = bf16(dropout(bf16(acc)) * silu'(z)),  z = aux (bf16)
     float zz[EW];
-    load_bf16_ew(reinterpret_cast<const bf16*>(e.aux) + (size_t)ms * ldo + n0, zz);
+    unpack_aux(auxc, zz);
 #pragma unroll
     for (int j = 0; j < EW; ++j) v[j] = bf16_round(v[j]);
     if (e.drop_keep != 0) dropout_ew(v, e, didx);
@@ -298,7 +327,7 @@ __device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int
     stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
   } else if (MODE == B2C_EPI_RELU_BWD) {
     float yy[EW];
-    load_bf16_ew(reinterpret_cast<const bf16*>(e.aux) + (size_t)ms * ldo + n0, yy);
+    unpack_aux(auxc, yy);
 #pragma unroll
     for (int j = 0; j < EW; ++j) v[j] = yy[j] > 0.f ? v[j] : 0.f;
     stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
@@ -489,12 +518,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       } else if (CONV == 3) {
         epi.out0 = reinterpret_cast<float*>(epi.out0) + (size_t)split * p.cv.C;  // tap-major columns
       }
-#pragma unroll 1
-      for (int c = cgrp; c < BN / EW; c += kEpiWarps / 4) {
-        uint32_t acc[EW];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * EW), acc);
+      // software pipeline over this warp's column chunks: the TMEM load and the bf16 side input of chunk i+1 are in
+      // flight while chunk i goes through the epilogue maths and the staged store
+      constexpr int kChunks = BN / EW / (kEpiWarps / 4);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      const bool atomic = (CONV == 0 && p.splits > 1);
+      uint32_t acc[2][EW];
+      AuxChunk auxc[2];
+      tmem_ld16(trow + (uint32_t)(cgrp * EW), acc[0]);
+      aux_prefetch<MODE>(auxc[0], epi, m, n0 + cgrp * EW, m_bound, p.N);
+#pragma unroll
+      for (int i = 0; i < kChunks; ++i) {
+        const int c = cgrp + i * (kEpiWarps / 4);
         tmem_ld_wait();
-        epilogue_chunk<MODE>(epi, m, n0 + c * EW, m_bound, p.N, acc, CONV == 0 && p.splits > 1, stg, lane);
+        if (i + 1 < kChunks) {
+          const int cn = c + kEpiWarps / 4;
+          tmem_ld16(trow + (uint32_t)(cn * EW), acc[(i + 1) & 1]);
+          aux_prefetch<MODE>(auxc[(i + 1) & 1], epi, m, n0 + cn * EW, m_bound, p.N);
+        }
+        epilogue_chunk<MODE>(epi, m, n0 + c * EW, m_bound, p.N, acc[i & 1], auxc[i & 1], atomic, stg, lane);
       }
       tc_fence_before();
       __syncwarp();

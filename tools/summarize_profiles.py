@@ -1,0 +1,87 @@
+"""Turns the scratch ncu outputs under gpurun_out/ into the tracked summaries under profiles/ (named per round).
+  python tools/summarize_profiles.py r01"""
+import collections
+import csv
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+out_dir = os.path.join(ROOT, "profiles")
+os.makedirs(out_dir, exist_ok=True)
+G = os.path.join(ROOT, "gpurun_out")
+
+
+def launches():
+    p = os.path.join(G, "launches.csv")
+    if not os.path.exists(p):
+        return
+    lines = [l for l in open(p) if l.startswith('"')]
+    r = csv.reader(lines)
+    hdr = next(r)
+    ix = {h: i for i, h in enumerate(hdr)}
+    tot, cnt = collections.defaultdict(float), collections.Counter()
+    for row in r:
+        try:
+            v = float(row[ix["Metric Value"]].replace(",", ""))
+        except Exception:
+            continue
+        u = row[ix["Metric Unit"]]
+        v = v / 1e3 if u == "ns" else (v * 1e3 if u == "ms" else v)
+        name = row[ix["Kernel Name"]]
+        m = re.search(r"gemm_tc_kernel<(.*?)>", name)
+        key = f"gemm_tc_kernel<{m.group(1)}>" if m else re.sub(r"<.*", "", name).replace("void ", "")[:80]
+        tot[key] += v
+        cnt[key] += 1
+    T = sum(tot.values())
+    with open(os.path.join(out_dir, f"{tag}_launches.md"), "w") as f:
+        f.write(f"# {tag}: ncu launch list of `bench.py --steps 1 --warmup 1` (first 6000 launches ≈ 3 fwd + 2.7 bwd steps, "
+                "32x30 s, Conformer-CTC-Large)\n\n")
+        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 6000` — per-launch times are cold-cache and "
+                "serialised: compare SHARES.  gemm_tc_kernel<BN, A_MN, B_MN, EPILOGUE, CONV>.\n\n")
+        f.write("| kernel | launches | total ms | share | avg us |\n|---|---:|---:|---:|---:|\n")
+        for k, v in sorted(tot.items(), key=lambda x: -x[1]):
+            if v / T < 0.001:
+                continue
+            f.write(f"| `{k}` | {cnt[k]} | {v/1e3:.2f} | {100*v/T:.1f}% | {v/cnt[k]:.1f} |\n")
+        f.write(f"\ntotal {T/1e3:.1f} ms over {sum(cnt.values())} launches\n")
+
+
+def ncu_raw(rep, name, pattern):
+    p = os.path.join(G, rep)
+    if not os.path.exists(p):
+        return
+    raw = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    if len(rows) < 3:
+        return
+    hdr, units = rows[0], rows[1]
+    want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+            "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+            "launch__registers_per_thread", "launch__grid_size", "launch__block_size"]
+    idx = [hdr.index(w) for w in want if w in hdr]
+    with open(os.path.join(out_dir, f"{tag}_{name}.csv"), "w") as f:
+        w = csv.writer(f)
+        w.writerow([hdr[i] for i in idx])
+        w.writerow([units[i] for i in idx])
+        for row in rows[2:]:
+            out = [row[i] for i in idx]
+            out[0] = re.sub(r"void |b2c::|\(.*", "", out[0])[:70]
+            w.writerow(out)
+
+
+launches()
+ncu_raw("prof_gemm.ncu-rep", "ncu_gemm", "gemm")
+ncu_raw("prof_attn.ncu-rep", "ncu_attn", "attn")
+ncu_raw("prof_ln.ncu-rep", "ncu_ln_dwconv", "ln")
+for f in ("bench.log",):
+    p = os.path.join(G, f)
+    if os.path.exists(p):
+        for line in open(p):
+            if line.startswith("{"):
+                json.dump(json.loads(line), open(os.path.join(out_dir, f"{tag}_bench.json"), "w"), indent=1)
+print(sorted(os.listdir(out_dir)))
