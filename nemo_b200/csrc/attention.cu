@@ -10,7 +10,7 @@
 // Round-1 implementation: warp-level mma.sync.m16n8k16 (bf16, fp32 accumulate) with the positional band of
 // 16+64-1 rows per warp multiplied on tensor cores and skewed through a per-warp shared-memory scratch.
 // (tcgen05/TMEM version of this kernel is the next optimisation step; see DESIGN.md.)
-#include "common.cuh"
+#include "attn_common.cuh"
 
 namespace b2c {
 
@@ -18,7 +18,6 @@ constexpr int BQ = 64;    // query rows per CTA (4 warps x 16)
 constexpr int BKV = 64;   // keys per inner tile
 constexpr int BAND = 80;  // 16 + 64 - 1 rounded up to a multiple of 16
 constexpr int SCR_PITCH = 84;
-constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -39,21 +38,6 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(smem_u32(p)));
 }
-
-struct AttnArgs {
-  const bf16* qkv;   // [B*T, 3d]
-  const bf16* pos;   // [2T-1, d]
-  const float* bias_u;
-  const float* bias_v;
-  const int32_t* lengths;
-  int B, T, H, d;
-  float scale;       // 1/sqrt(dk)
-  float drop_p;
-  unsigned int drop_keep;
-  float drop_scale;
-  unsigned long long seed;
-  unsigned int site;
-};
 
 // ---- tile loaders -------------------------------------------------------------------------------------------
 // rows [row0, row0+nrows) x DK columns of a [*, ld] bf16 matrix into smem (pitch DK+8); rows outside [0, limit) → 0
@@ -184,14 +168,6 @@ __device__ __forceinline__ void score_tile(float (&s)[8][4], const uint32_t (&qu
   }
 }
 
-// keep decisions for the element pair (i, j), (i, j+1) with j even: bit0 / bit1
-__device__ __forceinline__ uint32_t attn_keep2(const AttnArgs& a, uint64_t row_base, int j) {
-  const uint32_t hsh = dropout_hash(a.seed, a.site, (row_base + (uint64_t)j) >> 1);
-  return ((hsh & 0xFFFFu) < a.drop_keep ? 1u : 0u) | ((hsh >> 16) < a.drop_keep ? 2u : 0u);
-}
-__device__ __forceinline__ uint64_t attn_row_base(const AttnArgs& a, int b, int h, int i) {
-  return ((uint64_t)((b * a.H + h) * (int64_t)a.T + i)) * (uint64_t)((a.T + 1) & ~1);
-}
 __device__ __forceinline__ bool attn_keep(const AttnArgs& a, int b, int h, int i, int j) {
   // row pitch rounded up to even so the (j, j+1) pairs a thread owns share one hash
   const uint64_t idx = ((uint64_t)((b * a.H + h) * (int64_t)a.T + i)) * (uint64_t)((a.T + 1) & ~1) + (uint64_t)j;
@@ -792,7 +768,15 @@ extern "C" int b2c_relpos_attn_fwd(const void* qkv, const void* pos, const float
   AttnArgs a;
   int rc = fill_args(a, qkv, pos, bias_u, bias_v, lengths, B, T, h, dk, drop_p, seed, site);
   if (rc) return rc;
-  if (dk == 64) return launch_fwd<64>(a, reinterpret_cast<bf16*>(ctx), ctx_f32, lse, (cudaStream_t)stream);
+  if (dk == 64) {
+    static int impl = -1;  // B2C_ATTN_IMPL=mma selects the legacy mma.sync kernel (debug / A-B comparison)
+    if (impl < 0) {
+      const char* e = getenv("B2C_ATTN_IMPL");
+      impl = (e && !strcmp(e, "mma")) ? 1 : 0;
+    }
+    if (impl == 0) return launch_relpos_attn_fwd_tc(a, reinterpret_cast<bf16*>(ctx), ctx_f32, lse, (cudaStream_t)stream);
+    return launch_fwd<64>(a, reinterpret_cast<bf16*>(ctx), ctx_f32, lse, (cudaStream_t)stream);
+  }
   return launch_fwd<128>(a, reinterpret_cast<bf16*>(ctx), ctx_f32, lse, (cudaStream_t)stream);
 }
 
