@@ -55,54 +55,46 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clock + throttle reasons sampled DURING the timed region (B200_PROFILING.md) through NVML in a background thread.
-    NVML queries take a driver lock that stalls kernel submission (on some pool hosts a query costs ~100 ms: the
-    recipe's `nvidia-smi -lms 200`, or this thread at 5 Hz, tripled the step time), so the region is sampled sparsely:
-    once 0.15 s in, then every `period` seconds; the per-query cost is reported as `nvml_ms`."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md), read through NVML from the main thread
+    at the one moment it cannot perturb the measurement: right after the last timed step has been ENQUEUED, while the
+    GPU is still executing the queued work of the region.  (NVML queries hold a driver lock that blocks kernel
+    submission — up to ~150 ms per query on some pool hosts — so the recipe's `nvidia-smi -lms 200`, or a 5 Hz sampler
+    thread, stretched single steps from 87 ms to 245 ms.)"""
 
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index=0, period=0.4):
-        self.index, self.period, self.rows, self._stop, self.thr, self.err = index, period, [], False, None, None
-        self.cost = []
-
-    def start(self):
+    def __init__(self, index=0):
+        self.index, self.rows, self.cost, self.err, self.h, self.nv = index, [], [], None, None, None
         try:
             import pynvml
 
             pynvml.nvmlInit()
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
-            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-
-            def loop():
-                time.sleep(0.15)
-                while not self._stop:
-                    try:
-                        t0 = time.perf_counter()
-                        mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
-                        try:
-                            rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-                        except Exception:
-                            rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                        self.rows.append((mhz, rs))
-                        self.cost.append((time.perf_counter() - t0) * 1e3)
-                    except Exception as e:  # noqa: BLE001
-                        self.err = repr(e)
-                    t_end = time.perf_counter() + self.period
-                    while not self._stop and time.perf_counter() < t_end:
-                        time.sleep(0.02)
-
-            self.thr = threading.Thread(target=loop, daemon=True)
-            self.thr.start()
+            idx = int(vis.split(",")[index]) if vis and index < len(vis.split(",")) and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
         except Exception as e:  # noqa: BLE001
             self.err = repr(e)
 
-    def stop(self):
-        self._stop = True
-        if self.thr is not None:
-            self.thr.join(timeout=2)
+    def sample(self, n=3, gap=0.01):
+        if self.nv is None:
+            return
+        for _ in range(n):
+            try:
+                t0 = time.perf_counter()
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                try:
+                    rs = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((mhz, rs))
+                self.cost.append((time.perf_counter() - t0) * 1e3)
+            except Exception as e:  # noqa: BLE001
+                self.err = repr(e)
+            time.sleep(gap)
+
+    def result(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"nvml unavailable: {self.err}"]}
         sm = sorted(r[0] for r in self.rows)
@@ -112,7 +104,8 @@ class ClockSampler:
                 if rs & bit:
                     reasons.add(name)
         return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(self.max_mhz), "reasons": sorted(reasons),
-                "samples": len(sm), "nvml_ms": round(max(self.cost), 2) if self.cost else None}
+                "samples": len(sm), "nvml_ms": round(max(self.cost), 2) if self.cost else None,
+                "when": "after the last timed step was enqueued, GPU still executing the region"}
 
 
 # ------------------------------------------------------------------------------------------------ reference / CPU arm
@@ -241,7 +234,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(n, from_host, profile_gemm=False):
+    def timed(n, from_host, profile_gemm=False, sampler=None):
         barrier()
         if profile_gemm:
             import nemo_b200.encoder as E
@@ -258,6 +251,8 @@ def run_ours(args):
             marks.append(torch.cuda.Event(enable_timing=True))
             marks[-1].record()
         e1.record()
+        if sampler is not None:
+            sampler.sample()  # GPU is still busy with the enqueued steps; nothing is left to submit
         barrier()
         per_step.clear()
         prev = e0
@@ -275,11 +270,9 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step(wav_dev, len_dev, False)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    ms, launches = timed(args.steps, False)
-    clk = clocks.stop() if rank == 0 else None
+    clocks = ClockSampler(local) if rank == 0 else None
+    ms, launches = timed(args.steps, False, sampler=clocks)
+    clk = clocks.result() if rank == 0 else None
     step_ms_value = list(per_step)
     ms_e2e, _ = timed(args.steps, True)
     step_ms_e2e = list(per_step)

@@ -6,8 +6,10 @@
 //               128 x 64 score tile can touch (rel_shift folded into the band index, no [T, 2T-1] tensor anywhere)
 //   warp 1      MMA issuer (one thread):  S = (q+u) K^T  (N = 64),  R = (q+v) P_band^T  (N = 192),  O_j = P_j V  (N = 64)
 //   warp 2      TMEM allocator (512 columns: S | R | O)
-//   warps 4..7  softmax: thread = query row (TMEM lane).  bd[i, j] = R[i, j + 127 - i]: the per-row skew is a
-//               warp-uniform TMEM column offset plus a 5-stage register barrel shift by (31 - lane).
+//   warps 4..11 softmax: two threads per query row (TMEM lane), each owning 32 of the tile's 64 key columns and 32 of
+//               the 64 output columns; row maxima are exchanged through smem + a 64-thread named barrier.
+//               bd[i, j] = R[i, j + 127 - i]: the per-row skew is a warp-uniform TMEM column offset plus a 5-stage
+//               register barrel shift by (31 - lane).
 //               scores → mask(-1e4 semantics) → online softmax (exp2) → dropout → bf16 P tile written with the
 //               128-byte UMMA swizzle into smem → PV on the tensor cores; O_j is pulled from TMEM and accumulated in
 //               registers with the running-max correction.
@@ -25,7 +27,9 @@ constexpr int kQBytes = BQ * DK * 2;                      // 16 KB each (q+u, q+
 constexpr int kProbBytes = BQ * BKV * 2;                  // 16 KB
 constexpr int kOffQu = 0, kOffQv = kQBytes, kOffProb = 2 * kQBytes, kOffStage = 2 * kQBytes + kProbBytes;
 constexpr int kOffBar = kOffStage + kStages * kStageBytes;
-constexpr int kSmem = kOffBar + 256 + 1024;
+constexpr int kOffMax = kOffBar + 256;  // float [2][128] row-max / row-sum exchange between the two halves of a row
+constexpr int kSmem = kOffMax + 2 * 128 * 4 + 1024;
+constexpr int kThreads = 128 + 8 * 32;
 constexpr uint32_t kTmemS = 0, kTmemR = 64, kTmemO = 256;  // column offsets
 }  // namespace atc
 
@@ -54,7 +58,7 @@ __device__ __forceinline__ void st_sw128(uint8_t* tile, int row, int chunk, uint
   *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(atc::kThreads, 1)
 relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                           const __grid_constant__ CUtensorMap tmP, const AttnArgs a, bf16* __restrict__ ctx,
                           float* __restrict__ ctx32, float* __restrict__ lse_out) {
@@ -85,7 +89,7 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(sr_full, 1);
-    mbar_init(p_ready, 4);
+    mbar_init(p_ready, 8);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -180,7 +184,8 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       }
     }
   } else if (warp >= 4) {
-    const int q = warp & 3;
+    const int q = warp & 3;              // TMEM lane quarter (= warp id % 4)
+    const int half = (warp - 4) >> 2;    // which 32 key columns / 32 output columns of the row this thread owns
     const int il = q * 32 + lane;        // row inside the tile = TMEM lane
     const int row = i0 + il;
     const bool rvalid = row < len;
@@ -189,24 +194,24 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
     const int sh = 31 - lane;
     const float sc2 = a.scale * kLog2e;
     const uint64_t rbase = attn_row_base(a, b, h, row);
-    float o[DK];
+    float* xch = reinterpret_cast<float*>(smem + kOffMax);  // [2][128]
+    float o[32];
 #pragma unroll
-    for (int k = 0; k < DK; ++k) o[k] = 0.f;
+    for (int k = 0; k < 32; ++k) o[k] = 0.f;
     float m_run = -1e30f, l_run = 0.f;
     uint8_t* prob = smem + kOffProb;
 
     for (int jt = 0; jt < n_kv; ++jt) {
-      const int j0 = jt * BKV;
+      const int j0 = jt * BKV + half * 32;
       mbar_wait(sr_full, jt & 1);
       tc_fence_after();
-      float s[BKV];
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {
+      float s[32];
+      {
         uint32_t sa[32], x[64];
-        tmem_ld32(tlane + kTmemS + g * 32, sa);
-        tmem_ld64(tlane + kTmemR + (uint32_t)(cbase + g * 32), x);
+        tmem_ld32(tlane + kTmemS + half * 32, sa);
+        tmem_ld64(tlane + kTmemR + (uint32_t)(cbase + half * 32), x);
         tmem_ld_wait();
-        // barrel shift left by sh = 31 - lane: afterwards x[k] = R[cbase + g*32 + sh + k]
+        // barrel shift left by sh = 31 - lane: afterwards x[k] = R[cbase + half*32 + sh + k]
 #pragma unroll
         for (int k = 0; k < 48; ++k) x[k] = (sh & 16) ? x[k + 16] : x[k];
 #pragma unroll
@@ -219,30 +224,33 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
         for (int k = 0; k < 32; ++k) x[k] = (sh & 1) ? x[k + 1] : x[k];
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
-          const int j = j0 + g * 32 + k;
           const float v = (__uint_as_float(sa[k]) + __uint_as_float(x[k])) * sc2;
-          s[g * 32 + k] = (rvalid && j < len) ? v : -1e30f;
+          s[k] = (rvalid && j0 + k < len) ? v : -1e30f;
         }
       }
       float mx = -1e30f;
 #pragma unroll
-      for (int k = 0; k < BKV; ++k) mx = fmaxf(mx, s[k]);
+      for (int k = 0; k < 32; ++k) mx = fmaxf(mx, s[k]);
+      // row max across the two column halves: smem exchange + named barrier of the quarter's two warps
+      xch[half * 128 + il] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      mx = fmaxf(mx, xch[(half ^ 1) * 128 + il]);
       const float m_new = fmaxf(m_run, mx);
       const float corr = exp2f(m_run - m_new);
       // O_{j-1} (computed against the previous running max) joins the register accumulator, then everything is rescaled
       if (jt > 0) {
         mbar_wait(o_full, (jt - 1) & 1);
         tc_fence_after();
-        uint32_t ot[64];
-        tmem_ld64(tlane + kTmemO, ot);
+        uint32_t ot[32];
+        tmem_ld32(tlane + kTmemO + half * 32, ot);
         tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < DK; ++k) o[k] = (o[k] + __uint_as_float(ot[k])) * corr;
+        for (int k = 0; k < 32; ++k) o[k] = (o[k] + __uint_as_float(ot[k])) * corr;
       }
       m_run = m_new;
       float rs = 0.f;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         float p[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -258,38 +266,44 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
             p[k + 1] = (kp & 2u) ? p[k + 1] * a.drop_scale : 0.f;
           }
         }
-        st_sw128(prob, il, c, make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7])));
+        st_sw128(prob, il, half * 4 + c,
+                 make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7])));
       }
       l_run = l_run * corr + rs;
       fence_proxy_async();
       tc_fence_before();
-      __syncwarp();
+      // second barrier of the pair: both halves have read this tile's exchange slots before either overwrites them
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
       if (lane == 0) mbar_arrive(p_ready);
     }
     if (n_kv > 0) {
       mbar_wait(o_full, (n_kv - 1) & 1);
       tc_fence_after();
-      uint32_t ot[64];
-      tmem_ld64(tlane + kTmemO, ot);
+      uint32_t ot[32];
+      tmem_ld32(tlane + kTmemO + half * 32, ot);
       tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < DK; ++k) o[k] += __uint_as_float(ot[k]);
+      for (int k = 0; k < 32; ++k) o[k] += __uint_as_float(ot[k]);
     }
+    // total row sum = sum of the two halves (same running max)
+    xch[half * 128 + il] = l_run;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+    const float l_tot = l_run + xch[(half ^ 1) * 128 + il];
     if (row < T) {
-      const float inv = (rvalid && l_run > 0.f) ? 1.f / l_run : 0.f;  // fully-masked query rows output exactly 0
-      bf16* op = ctx + ((size_t)b * T + row) * a.d + h * DK;
+      const float inv = (rvalid && l_tot > 0.f) ? 1.f / l_tot : 0.f;  // fully-masked query rows output exactly 0
+      bf16* op = ctx + ((size_t)b * T + row) * a.d + h * DK + half * 32;
 #pragma unroll
-      for (int k = 0; k < DK; k += 8)
+      for (int k = 0; k < 32; k += 8)
         *reinterpret_cast<uint4*>(op + k) =
             make_uint4(pack_bf16(o[k] * inv, o[k + 1] * inv), pack_bf16(o[k + 2] * inv, o[k + 3] * inv),
                        pack_bf16(o[k + 4] * inv, o[k + 5] * inv), pack_bf16(o[k + 6] * inv, o[k + 7] * inv));
       if (ctx32) {
-        float* o32 = ctx32 + ((size_t)b * T + row) * a.d + h * DK;
+        float* o32 = ctx32 + ((size_t)b * T + row) * a.d + h * DK + half * 32;
 #pragma unroll
-        for (int k = 0; k < DK; k += 4)
+        for (int k = 0; k < 32; k += 4)
           *reinterpret_cast<float4*>(o32 + k) = make_float4(o[k] * inv, o[k + 1] * inv, o[k + 2] * inv, o[k + 3] * inv);
       }
-      if (lse_out) lse_out[((size_t)b * a.H + h) * T + row] = (rvalid && l_run > 0.f) ? m_run + log2f(l_run) : 0.f;
+      if (lse_out && half == 0) lse_out[((size_t)b * a.H + h) * T + row] = (rvalid && l_tot > 0.f) ? m_run + log2f(l_tot) : 0.f;
     }
   }
   tc_fence_before();
@@ -323,7 +337,7 @@ int launch_relpos_attn_fwd_tc(const AttnArgs& a, bf16* ctx, float* ctx32, float*
     B2C_CUDA(cudaFuncSetAttribute(relpos_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     set = true;
   }
-  relpos_attn_fwd_tc_kernel<<<dim3((a.T + BQ - 1) / BQ, a.H, a.B), 256, kSmem, st>>>(tk, tv, tp, a, ctx, ctx32, lse);
+  relpos_attn_fwd_tc_kernel<<<dim3((a.T + BQ - 1) / BQ, a.H, a.B), kThreads, kSmem, st>>>(tk, tv, tp, a, ctx, ctx32, lse);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
 }
