@@ -68,9 +68,10 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* sr_full = empty_bar + kStages;  // S and R of the current key tile are in TMEM
-  uint64_t* p_ready = sr_full + 1;          // softmax has consumed S/R (and O of the previous tile) and published P
+  uint64_t* p_ready = sr_full + 1;          // softmax has consumed O of the previous tile and published P
   uint64_t* o_full = p_ready + 1;           // O_j = P_j V is in TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+  uint64_t* sr_free = o_full + 1;           // S / R of the current tile are in registers: the next tile's may be issued
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sr_free + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -91,6 +92,7 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
     mbar_init(sr_full, 1);
     mbar_init(p_ready, 8);
     mbar_init(o_full, 1);
+    mbar_init(sr_free, 8);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -163,15 +165,18 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       tc_fence_after();
       issue_sr(0);
       for (int jt = 0; jt < n_kv; ++jt) {
-        mbar_wait(p_ready, jt & 1);
-        tc_fence_after();
         int nstage = stage + 1, nphase = phase;
         if (nstage == kStages) { nstage = 0; nphase ^= 1; }
-        if (jt + 1 < n_kv) {  // next tile's scores first: the softmax warps can start on them while PV_j runs
+        if (jt + 1 < n_kv) {
+          // as soon as the softmax warps hold S_j / R_j in registers, the next tile's scores go to the tensor cores:
+          // they are computed while the softmax / exp / dropout of tile j is still running
+          mbar_wait(sr_free, jt & 1);
           mbar_wait(&full_bar[nstage], nphase);
           tc_fence_after();
           issue_sr(nstage);
         }
+        mbar_wait(p_ready, jt & 1);
+        tc_fence_after();
         const uint32_t sv = smem_u32(smem + kOffStage + stage * kStageBytes) + kKBytes;
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k)
@@ -211,6 +216,9 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
         tmem_ld32(tlane + kTmemS + half * 32, sa);
         tmem_ld64(tlane + kTmemR + (uint32_t)(cbase + half * 32), x);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sr_free);
         // barrel shift left by sh = 31 - lane: afterwards x[k] = R[cbase + half*32 + sh + k]
 #pragma unroll
         for (int k = 0; k < 48; ++k) x[k] = (sh & 16) ? x[k + 16] : x[k];
