@@ -17,6 +17,7 @@ cpu_baseline = the fp32 oracle port timed on this box's host cores on a bounded 
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -235,6 +236,16 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(n, from_host, profile_gemm=False, sampler=None):
+        # manual garbage collection (cf. nemo/lightning/pytorch/callbacks/garbage_collection.py): a generational sweep in the
+        # middle of a step stalls kernel submission (one timed step in ~10 showed a >100 ms host-side gap without this)
+        gc.collect()
+        gc.disable()
+        try:
+            return _timed(n, from_host, profile_gemm, sampler)
+        finally:
+            gc.enable()
+
+    def _timed(n, from_host, profile_gemm, sampler):
         barrier()
         if profile_gemm:
             import nemo_b200.encoder as E

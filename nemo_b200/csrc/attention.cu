@@ -735,7 +735,7 @@ static int launch_fwd(const AttnArgs& a, bf16* ctx, float* ctx32, float* lse, cu
 
 template <int DK>
 static int launch_bwd(const AttnArgs& a, const bf16* ctx, const float* ctx32, const bf16* dctx, const float* lse, bf16* dqkv, float* dpos,
-                      float* dbu, float* dbv, bf16* ws_ds, bf16* ws_p, int Tp, cudaStream_t st) {
+                      float* dbu, float* dbv, bf16* ws_ds, bf16* ws_p, bf16* ws_qu, int Tp, cudaStream_t st) {
   const size_t smem1 = smem_q<DK>();
   const size_t smem2 = 2 * ((size_t)2 * 64 * (DK + 8) * 2 + (size_t)2 * 64 * (BKV + 8) * 2);
   const size_t smem3 = (size_t)64 * (DK + 8) * 2 + (size_t)64 * 72 * 2;
@@ -747,10 +747,26 @@ static int launch_bwd(const AttnArgs& a, const bf16* ctx, const float* ctx32, co
     set = true;
   }
   const int qt = (a.T + BQ - 1) / BQ;
-  relpos_attn_bwd_q_kernel<DK><<<dim3(qt, a.H, a.B), 128, smem1, st>>>(a, ctx, ctx32, dctx, lse, dqkv, dbu, dbv, ws_ds, ws_p, Tp);
-  B2C_LAUNCH_CHECK();
-  relpos_attn_bwd_kv_kernel<DK><<<dim3(qt, a.H, a.B), 128, smem2, st>>>(a, dctx, ws_ds, ws_p, dqkv, Tp);
-  B2C_LAUNCH_CHECK();
+  // B2C_ATTN_IMPL=mma selects the legacy mma.sync kernels, =mmakv only the legacy key-side kernel (A/B comparison)
+  static int impl = -1;
+  if (impl < 0) {
+    const char* e = getenv("B2C_ATTN_IMPL");
+    impl = (e && !strcmp(e, "mma")) ? 1 : (e && !strcmp(e, "mmakv")) ? 2 : 0;
+  }
+  if (DK == 64 && impl != 1) {
+    int rc = launch_relpos_attn_bwd_q_tc(a, ctx, ctx32, dctx, lse, dqkv, dbu, dbv, ws_ds, ws_p, ws_qu, Tp, st);
+    if (rc) return rc;
+  } else {
+    relpos_attn_bwd_q_kernel<DK><<<dim3(qt, a.H, a.B), 128, smem1, st>>>(a, ctx, ctx32, dctx, lse, dqkv, dbu, dbv, ws_ds, ws_p, Tp);
+    B2C_LAUNCH_CHECK();
+  }
+  if (DK == 64 && impl == 0) {
+    int rc = launch_relpos_attn_bwd_kv_tc(a, dctx, ws_ds, ws_p, ws_qu, dqkv, Tp, st);
+    if (rc) return rc;
+  } else {
+    relpos_attn_bwd_kv_kernel<DK><<<dim3(qt, a.H, a.B), 128, smem2, st>>>(a, dctx, ws_ds, ws_p, dqkv, Tp);
+    B2C_LAUNCH_CHECK();
+  }
   const int b_per_cta = 2;
   relpos_attn_bwd_pos_kernel<DK><<<dim3((2 * a.T - 1 + 63) / 64, a.H, (a.B + b_per_cta - 1) / b_per_cta), 128, smem3, st>>>(
       a, ws_ds, dpos, Tp, b_per_cta);
@@ -780,10 +796,10 @@ extern "C" int b2c_relpos_attn_fwd(const void* qkv, const void* pos, const float
   return launch_fwd<128>(a, reinterpret_cast<bf16*>(ctx), ctx_f32, lse, (cudaStream_t)stream);
 }
 
-/* workspace: 2 * B*h*T*Tp bf16 with Tp = (T+7)&~7 */
+/* workspace: dS and P_dropped, 2 * B*h*T*Tp bf16 with Tp = (T+7)&~7, then (q + pos_bias_u) [B,T,h*dk] bf16 (dk <= 128) */
 extern "C" size_t b2c_relpos_attn_bwd_workspace(int B, int T, int h) {
   const size_t Tp = (size_t)((T + 7) & ~7);
-  return 2 * (size_t)B * h * T * Tp * 2;
+  return 2 * (size_t)B * h * T * Tp * 2 + (size_t)B * T * h * 128 * 2;
 }
 
 extern "C" int b2c_relpos_attn_bwd(const void* qkv, const void* pos, const float* bias_u, const float* bias_v,
@@ -798,9 +814,10 @@ extern "C" int b2c_relpos_attn_bwd(const void* qkv, const void* pos, const float
   B2C_REQUIRE(workspace && workspace_bytes >= b2c_relpos_attn_bwd_workspace(B, T, h), "relpos_attn_bwd: workspace too small");
   bf16* ws_ds = reinterpret_cast<bf16*>(workspace);
   bf16* ws_p = ws_ds + (size_t)B * h * T * Tp;
+  bf16* ws_qu = ws_p + (size_t)B * h * T * Tp;
   if (dk == 64)
     return launch_bwd<64>(a, reinterpret_cast<const bf16*>(ctx), ctx_f32, reinterpret_cast<const bf16*>(dctx), lse,
-                          reinterpret_cast<bf16*>(dqkv), dpos_f32, dbias_u, dbias_v, ws_ds, ws_p, Tp, (cudaStream_t)stream);
+                          reinterpret_cast<bf16*>(dqkv), dpos_f32, dbias_u, dbias_v, ws_ds, ws_p, ws_qu, Tp, (cudaStream_t)stream);
   return launch_bwd<128>(a, reinterpret_cast<const bf16*>(ctx), ctx_f32, reinterpret_cast<const bf16*>(dctx), lse,
-                         reinterpret_cast<bf16*>(dqkv), dpos_f32, dbias_u, dbias_v, ws_ds, ws_p, Tp, (cudaStream_t)stream);
+                         reinterpret_cast<bf16*>(dqkv), dpos_f32, dbias_u, dbias_v, ws_ds, ws_p, ws_qu, Tp, (cudaStream_t)stream);
 }

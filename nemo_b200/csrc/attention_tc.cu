@@ -257,6 +257,7 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       }
       m_run = m_new;
       float rs = 0.f;
+      uint32_t kbase = 0;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float p[8];
@@ -267,11 +268,12 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
           rs += p[k];
         }
         if (a.drop_keep != 0) {
+          if ((c & 1) == 0) kbase = attn_keep_base(a, rbase, j0 + c * 8);
 #pragma unroll
           for (int k = 0; k < 8; k += 2) {
-            const uint32_t kp = attn_keep2(a, rbase, j0 + c * 8 + k);
-            p[k] = (kp & 1u) ? p[k] * a.drop_scale : 0.f;
-            p[k + 1] = (kp & 2u) ? p[k + 1] * a.drop_scale : 0.f;
+            const uint32_t hw = dropout_word(kbase, (c & 1) * 4 + (k >> 1));
+            p[k] = ((hw & 0xFFFFu) < a.drop_keep) ? p[k] * a.drop_scale : 0.f;
+            p[k + 1] = ((hw >> 16) < a.drop_keep) ? p[k + 1] * a.drop_scale : 0.f;
           }
         }
         st_sw128(prob, il, half * 4 + c,
@@ -346,6 +348,558 @@ int launch_relpos_attn_fwd_tc(const AttnArgs& a, bf16* ctx, float* ctx32, float*
     set = true;
   }
   relpos_attn_fwd_tc_kernel<<<dim3((a.T + BQ - 1) / BQ, a.H, a.B), kThreads, kSmem, st>>>(tk, tv, tp, a, ctx, ctx32, lse);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+
+// =============================================================================================== backward (query side)
+// Same tiling as the forward: 128 query rows per CTA, 64-key tiles, 2 softmax threads per row.  Per tile the tensor cores
+// produce S, R (positional band) and dP = dO V^T into TMEM; the softmax warps rebuild P = exp2(S - lse), form
+// dS = P * (dP - delta) / sqrt(dk), publish it twice in shared memory — as the [128 x 64] A operand of dQ_u += dS K and,
+// un-skewed (row i shifted by 127 - i), as the [128 x 192] A operand of dQ_v += dS~ P_band — and stage dS / P_dropped in
+// HBM for the key-side and position-side kernels.  dQ_u and dQ_v accumulate in TMEM over the whole key loop.
+namespace atb {
+constexpr int BQ = 128, BKV = 64, DK = 64, BAND = 192;
+constexpr int kStages = 2;
+constexpr int kKBytes = BKV * DK * 2, kVBytes = BKV * DK * 2, kPBytes = BAND * DK * 2;
+constexpr int kStageBytes = kKBytes + kVBytes + kPBytes;  // 40 KB
+constexpr int kTile = BQ * DK * 2;                        // 16 KB: one [128 x 64] bf16 K-major tile
+constexpr int kOffQu = 0, kOffQv = kTile, kOffDO = 2 * kTile, kOffDS = 3 * kTile, kOffDSU = 4 * kTile;  // dS~: 3 tiles
+constexpr int kOffStage = 7 * kTile;
+constexpr int kOffBar = kOffStage + kStages * kStageBytes;
+constexpr int kOffXch = kOffBar + 256;            // float [2][128]
+constexpr int kOffXch2 = kOffXch + 2 * 128 * 4;   // uint4 [2][128]: half 0 → half 1 boundary chunk of the un-skewed row
+constexpr int kSmem = kOffXch2 + 2 * 128 * 16 + 1024;
+constexpr int kThreads = 128 + 8 * 32;
+constexpr uint32_t kTmS = 0, kTmR = 64, kTmDP = 256, kTmDQU = 320, kTmDQV = 384;
+}  // namespace atb
+
+__global__ void __launch_bounds__(atb::kThreads, 1)
+relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                            const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmDO, const AttnArgs a,
+                            const float* __restrict__ ctx32, const bf16* __restrict__ ctx, const bf16* __restrict__ dctx,
+                            const float* __restrict__ lse, bf16* __restrict__ dqkv, float* __restrict__ dbias_u,
+                            float* __restrict__ dbias_v, bf16* __restrict__ ws_ds, bf16* __restrict__ ws_p,
+                            bf16* __restrict__ ws_qu, int Tp) {
+  using namespace atb;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* srd_full = empty_bar + kStages;  // S, R, dP of the current tile are in TMEM
+  uint64_t* srd_free = srd_full + 1;         // ... and have been pulled into registers
+  uint64_t* ds_ready = srd_free + 1;         // dS / dS~ of the current tile are in shared memory
+  uint64_t* dq_done = ds_ready + 1;          // the dQ MMAs that read them have retired
+  uint64_t* do_full = dq_done + 1;           // dO tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(do_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int T = a.T, ld = 3 * a.d;
+  const int len = a.lengths ? min(a.lengths[b], T) : T;
+  const int n_kv = (len + BKV - 1) / BKV;
+  const int n_kv_all = (T + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmP); tma_prefetch_desc(&tmDO);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(srd_full, 1); mbar_init(srd_free, 8); mbar_init(ds_ready, 8); mbar_init(dq_done, 1); mbar_init(do_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  {
+    // (q+u), (q+v) A tiles; zero the un-skew tile (each row only ever writes its own fixed 64-column window)
+    const bf16* qb = a.qkv + (size_t)b * T * ld + h * DK;
+    const float* bu = a.bias_u + h * DK;
+    const float* bv = a.bias_v + h * DK;
+    for (int idx = threadIdx.x; idx < BQ * 8; idx += blockDim.x) {
+      const int r = idx >> 3, ck = idx & 7;
+      uint4 qu = make_uint4(0, 0, 0, 0), qv = make_uint4(0, 0, 0, 0);
+      if (i0 + r < T) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(qb + (size_t)(i0 + r) * ld + ck * 8);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+        uint32_t ou[4], ov[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = unpack_bf16(w[k]);
+          const int c = ck * 8 + 2 * k;
+          ou[k] = pack_bf16(f.x + bu[c], f.y + bu[c + 1]);
+          ov[k] = pack_bf16(f.x + bv[c], f.y + bv[c + 1]);
+        }
+        qu = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+        qv = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+        if (ws_qu) *reinterpret_cast<uint4*>(ws_qu + ((size_t)b * T + i0 + r) * a.d + h * DK + ck * 8) = qu;
+      }
+      st_sw128(smem + kOffQu, r, ck, qu);
+      st_sw128(smem + kOffQv, r, ck, qv);
+    }
+    for (int i = threadIdx.x; i < 3 * kTile / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(smem + kOffDSU)[i] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && n_kv > 0) {
+      mbar_expect_tx(do_full, kTile);
+      tma_load_3d(smem + kOffDO, &tmDO, do_full, h * DK, i0, b);
+      int stage = 0, phase = 0;
+      for (int jt = 0; jt < n_kv; ++jt) {
+        const int j0 = jt * BKV;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + kOffStage + stage * kStageBytes;
+        mbar_expect_tx(&full_bar[stage], kStageBytes);
+        tma_load_3d(st, &tmK, &full_bar[stage], a.d + h * DK, j0, b);
+        tma_load_3d(st + kKBytes, &tmV, &full_bar[stage], 2 * a.d + h * DK, j0, b);
+        tma_load_2d(st + kKBytes + kVBytes, &tmP, &full_bar[stage], h * DK, T - 1 - (i0 + BQ - 1) + j0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_kv > 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_r = umma_idesc_bf16(BQ, BAND, 0, 0);
+      constexpr uint32_t idesc_q = umma_idesc_bf16(BQ, DK, 0, 1);  // B = K tile / P band as [k rows][dcol contiguous]
+      const uint32_t s_qu = smem_u32(smem + kOffQu), s_qv = smem_u32(smem + kOffQv), s_do = smem_u32(smem + kOffDO);
+      const uint32_t s_ds = smem_u32(smem + kOffDS), s_dsu = smem_u32(smem + kOffDSU);
+      auto issue_srd = [&](int stage) {
+        const uint32_t sk = smem_u32(smem + kOffStage + stage * kStageBytes);
+        const uint32_t sv = sk + kKBytes, sp = sv + kVBytes;
+#pragma unroll
+        for (int k = 0; k < DK / 16; ++k) {
+          umma_bf16(tmem_base + kTmS, umma_desc_sw128(s_qu + k * 32, 16, 1024), umma_desc_sw128(sk + k * 32, 16, 1024), idesc_s, k > 0);
+          umma_bf16(tmem_base + kTmR, umma_desc_sw128(s_qv + k * 32, 16, 1024), umma_desc_sw128(sp + k * 32, 16, 1024), idesc_r, k > 0);
+          umma_bf16(tmem_base + kTmDP, umma_desc_sw128(s_do + k * 32, 16, 1024), umma_desc_sw128(sv + k * 32, 16, 1024), idesc_s, k > 0);
+        }
+        umma_commit(srd_full);
+      };
+      int stage = 0, phase = 0;
+      mbar_wait(do_full, 0);
+      mbar_wait(&full_bar[0], 0);
+      tc_fence_after();
+      issue_srd(0);
+      for (int jt = 0; jt < n_kv; ++jt) {
+        int nstage = stage + 1, nphase = phase;
+        if (nstage == kStages) { nstage = 0; nphase ^= 1; }
+        if (jt + 1 < n_kv) {
+          mbar_wait(srd_free, jt & 1);
+          mbar_wait(&full_bar[nstage], nphase);
+          tc_fence_after();
+          issue_srd(nstage);
+        }
+        mbar_wait(ds_ready, jt & 1);
+        tc_fence_after();
+        const uint32_t sk = smem_u32(smem + kOffStage + stage * kStageBytes);
+        const uint32_t sp = sk + kKBytes + kVBytes;
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)   // dQ_u += dS (128 x 64 keys) * K (64 keys x 64)
+          umma_bf16(tmem_base + kTmDQU, umma_desc_sw128(s_ds + k * 32, 16, 1024), umma_desc_sw128(sk + k * 2048, 64 * BKV * 2, 1024),
+                    idesc_q, (jt > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < BAND / 16; ++k)  // dQ_v += dS~ (128 x 192 band) * P_band (192 x 64)
+          umma_bf16(tmem_base + kTmDQV, umma_desc_sw128(s_dsu + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
+                    umma_desc_sw128(sp + k * 2048, 64 * BAND * 2, 1024), idesc_q, (jt > 0 || k > 0) ? 1u : 0u);
+        umma_commit(dq_done);
+        umma_commit(&empty_bar[stage]);
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const int il = q * 32 + lane, row = i0 + il;
+    const bool rvalid = row < len;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int cbase = 96 - 32 * q, sh = 31 - lane;
+    const float sc2 = a.scale * kLog2e;
+    const uint64_t rbase = attn_row_base(a, b, h, row);
+    float* xch = reinterpret_cast<float*>(smem + kOffXch);
+    // delta_i = sum_d dO[i,d] * O[i,d] (fp32 O when available) — each half sums its 32 columns, then exchange
+    float dpart = 0.f, lse2 = 0.f;
+    if (row < T) {
+      const bf16* dp = dctx + ((size_t)b * T + row) * a.d + h * DK + half * 32;
+      if (ctx32) {
+        const float* o32 = ctx32 + ((size_t)b * T + row) * a.d + h * DK + half * 32;
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          const float2 y = unpack_bf16(*reinterpret_cast<const uint32_t*>(dp + k));
+          dpart += o32[k] * y.x + o32[k + 1] * y.y;
+        }
+      } else {
+        const bf16* op = ctx + ((size_t)b * T + row) * a.d + h * DK + half * 32;
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(op + k));
+          const float2 y = unpack_bf16(*reinterpret_cast<const uint32_t*>(dp + k));
+          dpart += x.x * y.x + x.y * y.y;
+        }
+      }
+      lse2 = lse[((size_t)b * a.H + h) * T + row];
+    }
+    xch[half * 128 + il] = dpart;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+    const float delta = dpart + xch[(half ^ 1) * 128 + il];
+    bf16* wds = ws_ds + ((size_t)(b * a.H + h) * T) * Tp;
+    bf16* wp = ws_p + ((size_t)(b * a.H + h) * T) * Tp;
+    uint8_t* s_ds = smem + kOffDS;
+    uint8_t* s_dsu = smem + kOffDSU;
+
+    for (int jt = 0; jt < n_kv; ++jt) {
+      const int j0 = jt * BKV + half * 32;
+      mbar_wait(srd_full, jt & 1);
+      tc_fence_after();
+      float ds[32], pd[32];
+      {
+        uint32_t sa[32], x[64], dpv[32];
+        tmem_ld32(tlane + kTmS + half * 32, sa);
+        tmem_ld64(tlane + kTmR + (uint32_t)(cbase + half * 32), x);
+        tmem_ld32(tlane + kTmDP + half * 32, dpv);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(srd_free);
+#pragma unroll
+        for (int k = 0; k < 48; ++k) x[k] = (sh & 16) ? x[k + 16] : x[k];
+#pragma unroll
+        for (int k = 0; k < 40; ++k) x[k] = (sh & 8) ? x[k + 8] : x[k];
+#pragma unroll
+        for (int k = 0; k < 36; ++k) x[k] = (sh & 4) ? x[k + 4] : x[k];
+#pragma unroll
+        for (int k = 0; k < 34; ++k) x[k] = (sh & 2) ? x[k + 2] : x[k];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) x[k] = (sh & 1) ? x[k + 1] : x[k];
+#pragma unroll
+        uint32_t kbase = 0;
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          uint32_t keep = 3u;
+          if (a.drop_keep != 0) {
+            if ((k & 15) == 0) kbase = attn_keep_base(a, rbase, j0 + k);
+            const uint32_t hw = dropout_word(kbase, (k & 15) >> 1);
+            keep = ((hw & 0xFFFFu) < a.drop_keep ? 1u : 0u) | ((hw >> 16) < a.drop_keep ? 2u : 0u);
+          }
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const bool valid = rvalid && (j0 + k + e < len);
+            const float sv = (__uint_as_float(sa[k + e]) + __uint_as_float(x[k + e])) * sc2;
+            const float p = valid ? exp2f(sv - lse2) : 0.f;
+            const bool kp = (keep >> e) & 1u;
+            pd[k + e] = kp ? p * a.drop_scale : 0.f;
+            const float dpe = kp ? __uint_as_float(dpv[k + e]) * a.drop_scale : 0.f;
+            ds[k + e] = p * (dpe - delta) * a.scale;
+          }
+        }
+      }
+      // the previous tile's dQ MMAs must have finished reading the dS / dS~ tiles before they are overwritten
+      if (jt > 0) mbar_wait(dq_done, (jt - 1) & 1);
+      // dS → A operand tile (K-major, swizzled) and → HBM staging (dS, P_dropped)
+      uint32_t dsp[16], pdp[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        dsp[k] = pack_bf16(ds[2 * k], ds[2 * k + 1]);
+        pdp[k] = pack_bf16(pd[2 * k], pd[2 * k + 1]);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        st_sw128(s_ds, il, half * 4 + c, make_uint4(dsp[4 * c], dsp[4 * c + 1], dsp[4 * c + 2], dsp[4 * c + 3]));
+      if (row < T) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (j0 + c * 8 < Tp) {
+            *reinterpret_cast<uint4*>(wds + (size_t)row * Tp + j0 + c * 8) = make_uint4(dsp[4 * c], dsp[4 * c + 1], dsp[4 * c + 2], dsp[4 * c + 3]);
+            *reinterpret_cast<uint4*>(wp + (size_t)row * Tp + j0 + c * 8) = make_uint4(pdp[4 * c], pdp[4 * c + 1], pdp[4 * c + 2], pdp[4 * c + 3]);
+          }
+        }
+      }
+      // un-skewed copy: dS~[il][x] with x = j_local + 127 - il (a fixed 64-column window per row; the rest stays zero).
+      // x = half*32 + cbase + sh + k: the 16-byte chunk part of the shift is address arithmetic, the remaining
+      // (sh & 7) elements are a half-word funnel shift plus a 2-stage word barrel shift of the packed row.  The two
+      // halves of a row meet inside one chunk: half 0 hands its last (partial) chunk to half 1, which merges it.
+      {
+        const int es = sh & 7;
+        const uint32_t odd16 = (uint32_t)(es & 1) * 16u, wsh = (uint32_t)es >> 1;
+        uint32_t e[21];
+        e[0] = __funnelshift_l(0u, dsp[0], odd16);
+#pragma unroll
+        for (int k = 1; k < 16; ++k) e[k] = __funnelshift_l(dsp[k - 1], dsp[k], odd16);
+        e[16] = __funnelshift_l(dsp[15], 0u, odd16);
+        e[17] = e[18] = e[19] = e[20] = 0u;
+#pragma unroll
+        for (int k = 19; k >= 2; --k) e[k] = (wsh & 2u) ? e[k - 2] : e[k];
+        if (wsh & 2u) e[0] = e[1] = 0u;
+#pragma unroll
+        for (int k = 19; k >= 1; --k) e[k] = (wsh & 1u) ? e[k - 1] : e[k];
+        if (wsh & 1u) e[0] = 0u;
+        const int cid0 = half * 4 + (cbase >> 3) + (sh >> 3);
+        uint4* xq = reinterpret_cast<uint4*>(smem + kOffXch2) + (jt & 1) * 128 + il;
+        if (half == 0) *xq = make_uint4(e[16], e[17], e[18], e[19]);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        if (half == 1) {
+          const uint4 lo = *xq;
+          e[0] |= lo.x; e[1] |= lo.y; e[2] |= lo.z; e[3] |= lo.w;
+        }
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          if (c < 4 || half == 1) {
+            const int cid = cid0 + c;
+            st_sw128(s_dsu + (cid >> 3) * kTile, il, cid & 7, make_uint4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]));
+          }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_ready);
+    }
+    // key tiles entirely beyond the valid length: dS = P = 0 in the staging buffers
+    if (row < T) {
+      for (int j = n_kv * BKV + half * 32; j < n_kv_all * BKV; j += 64)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (j + c * 8 < Tp) {
+            *reinterpret_cast<uint4*>(wds + (size_t)row * Tp + j + c * 8) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(wp + (size_t)row * Tp + j + c * 8) = make_uint4(0, 0, 0, 0);
+          }
+    }
+    // dq = dQ_u + dQ_v; d(pos_bias_u/v) = column sums over rows
+    float du[32], dv[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) du[k] = dv[k] = 0.f;
+    if (n_kv > 0) {
+      mbar_wait(dq_done, (n_kv - 1) & 1);
+      tc_fence_after();
+      uint32_t t0[32], t1[32];
+      tmem_ld32(tlane + kTmDQU + half * 32, t0);
+      tmem_ld32(tlane + kTmDQV + half * 32, t1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) { du[k] = __uint_as_float(t0[k]); dv[k] = __uint_as_float(t1[k]); }
+    }
+    if (row < T) {
+      bf16* op = dqkv + ((size_t)b * T + row) * ld + h * DK + half * 32;
+#pragma unroll
+      for (int k = 0; k < 32; k += 8)
+        *reinterpret_cast<uint4*>(op + k) =
+            make_uint4(pack_bf16(du[k] + dv[k], du[k + 1] + dv[k + 1]), pack_bf16(du[k + 2] + dv[k + 2], du[k + 3] + dv[k + 3]),
+                       pack_bf16(du[k + 4] + dv[k + 4], du[k + 5] + dv[k + 5]), pack_bf16(du[k + 6] + dv[k + 6], du[k + 7] + dv[k + 7]));
+    }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const float su = warp_sum(du[k]), sv2 = warp_sum(dv[k]);  // rows >= len contribute exact zeros
+      if (lane == 0) {
+        atomicAdd(dbias_u + h * DK + half * 32 + k, su);
+        atomicAdd(dbias_v + h * DK + half * 32 + k, sv2);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+int launch_relpos_attn_bwd_q_tc(const AttnArgs& a, const bf16* ctx, const float* ctx32, const bf16* dctx, const float* lse,
+                                bf16* dqkv, float* dbu, float* dbv, bf16* ws_ds, bf16* ws_p, bf16* ws_qu, int Tp, cudaStream_t st) {
+  using namespace atb;
+  B2C_REQUIRE(a.d % 8 == 0 && a.d / a.H == DK && Tp % 8 == 0, "relpos_attn_bwd_q_tc: head dim must be 64");
+  CUtensorMap tk, tv, tp, tdo;
+  {
+    uint64_t dims[3] = {(uint64_t)3 * a.d, (uint64_t)a.T, (uint64_t)a.B};
+    uint64_t strides[2] = {(uint64_t)3 * a.d * 2, (uint64_t)a.T * 3 * a.d * 2};
+    uint32_t box[3] = {(uint32_t)DK, (uint32_t)BKV, 1}, es[3] = {1, 1, 1};
+    int rc = make_tmap(&tk, a.qkv, 2, 3, dims, strides, box, es, 1);
+    if (rc) return rc;
+    rc = make_tmap(&tv, a.qkv, 2, 3, dims, strides, box, es, 1);
+    if (rc) return rc;
+    uint64_t pd[2] = {(uint64_t)a.d, (uint64_t)(2 * a.T - 1)}, ps[1] = {(uint64_t)a.d * 2};
+    uint32_t pb[2] = {(uint32_t)DK, (uint32_t)BAND}, pe[2] = {1, 1};
+    rc = make_tmap(&tp, a.pos, 2, 2, pd, ps, pb, pe, 1);
+    if (rc) return rc;
+    uint64_t dd[3] = {(uint64_t)a.d, (uint64_t)a.T, (uint64_t)a.B};
+    uint64_t dstr[2] = {(uint64_t)a.d * 2, (uint64_t)a.T * a.d * 2};
+    uint32_t dbox[3] = {(uint32_t)DK, (uint32_t)BQ, 1};
+    rc = make_tmap(&tdo, dctx, 2, 3, dd, dstr, dbox, es, 1);
+    if (rc) return rc;
+  }
+  static bool set = false;
+  if (!set) {
+    B2C_CUDA(cudaFuncSetAttribute(relpos_attn_bwd_q_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    set = true;
+  }
+  relpos_attn_bwd_q_tc_kernel<<<dim3((a.T + BQ - 1) / BQ, a.H, a.B), kThreads, kSmem, st>>>(
+      tk, tv, tp, tdo, a, ctx32, ctx, dctx, lse, dqkv, dbu, dbv, ws_ds, ws_p, ws_qu, Tp);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+
+// =============================================================================================== backward (key side)
+// dK[j,:] = sum_i dS[i,j] (q_i+u),  dV[j,:] = sum_i Pd[i,j] dO[i,:] from the staged bf16 dS / P_dropped tiles: a pure
+// TMA → tcgen05 stream.  CTA = 128 keys of one (b,h); per 64-query tile both operands are used exactly as they lie in HBM
+// (A = dS^T / Pd^T: keys contiguous → MN-major, B = (q+u) / dO: channels contiguous → MN-major).  2 CTAs per SM.
+namespace akv {
+constexpr int BK = 128, BQ = 64, DK = 64;
+constexpr int kStages = 2;
+constexpr int kHalf = BQ * 64 * 2;                    // 8 KB: [64 queries][64 keys or channels]
+constexpr int kStageBytes = 6 * kHalf;                // dS (2 key chunks) | P (2) | q+u | dO = 48 KB
+constexpr int kOffBar = kStages * kStageBytes;
+constexpr int kSmem = kOffBar + 128 + 1024;
+constexpr int kThreads = 256;
+}  // namespace akv
+
+__global__ void __launch_bounds__(akv::kThreads, 2)
+relpos_attn_bwd_kv_tc_kernel(const __grid_constant__ CUtensorMap tmDS, const __grid_constant__ CUtensorMap tmPD,
+                             const __grid_constant__ CUtensorMap tmQU, const __grid_constant__ CUtensorMap tmDO, const AttnArgs a,
+                             bf16* __restrict__ dqkv) {
+  using namespace akv;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* acc_full = empty_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j0 = blockIdx.x * BK, h = blockIdx.y, b = blockIdx.z;
+  const int T = a.T, ld = 3 * a.d;
+  const int len = a.lengths ? min(a.lengths[b], T) : T;
+  const int n_q = (j0 < len) ? (len + BQ - 1) / BQ : 0;  // keys beyond the length have dS = P = 0 everywhere
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDS); tma_prefetch_desc(&tmPD); tma_prefetch_desc(&tmQU); tma_prefetch_desc(&tmDO);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      const int bh = b * a.H + h;
+      for (int it = 0; it < n_q; ++it) {
+        const int i0 = it * BQ;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * kStageBytes;
+        mbar_expect_tx(&full_bar[stage], kStageBytes);
+        tma_load_3d(st, &tmDS, &full_bar[stage], j0, i0, bh);
+        tma_load_3d(st + kHalf, &tmDS, &full_bar[stage], j0 + 64, i0, bh);
+        tma_load_3d(st + 2 * kHalf, &tmPD, &full_bar[stage], j0, i0, bh);
+        tma_load_3d(st + 3 * kHalf, &tmPD, &full_bar[stage], j0 + 64, i0, bh);
+        tma_load_3d(st + 4 * kHalf, &tmQU, &full_bar[stage], h * DK, i0, b);
+        tma_load_3d(st + 5 * kHalf, &tmDO, &full_bar[stage], h * DK, i0, b);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && n_q > 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BK, DK, 1, 1);
+      int stage = 0, phase = 0;
+      for (int it = 0; it < n_q; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t s0 = smem_u32(smem + stage * kStageBytes);
+#pragma unroll
+        for (int k = 0; k < BQ / 16; ++k) {
+          umma_bf16(tmem_base, umma_desc_sw128(s0 + k * 2048, kHalf, 1024), umma_desc_sw128(s0 + 4 * kHalf + k * 2048, kHalf, 1024),
+                    idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_base + 64, umma_desc_sw128(s0 + 2 * kHalf + k * 2048, kHalf, 1024),
+                    umma_desc_sw128(s0 + 5 * kHalf + k * 2048, kHalf, 1024), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(acc_full);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int j = j0 + q * 32 + lane;
+    uint32_t dk[64], dv[32];
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (n_q > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      tmem_ld64(tlane, dk);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int k = 0; k < 64; ++k) dk[k] = 0u;
+    }
+    if (j < T) {
+      bf16* op = dqkv + ((size_t)b * T + j) * ld + a.d + h * DK;
+#pragma unroll
+      for (int k = 0; k < 64; k += 8)
+        *reinterpret_cast<uint4*>(op + k) = make_uint4(
+            pack_bf16(__uint_as_float(dk[k]), __uint_as_float(dk[k + 1])), pack_bf16(__uint_as_float(dk[k + 2]), __uint_as_float(dk[k + 3])),
+            pack_bf16(__uint_as_float(dk[k + 4]), __uint_as_float(dk[k + 5])), pack_bf16(__uint_as_float(dk[k + 6]), __uint_as_float(dk[k + 7])));
+    }
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      if (n_q > 0) {
+        tmem_ld32(tlane + 64 + hf * 32, dv);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) dv[k] = 0u;
+      }
+      if (j < T) {
+        bf16* op = dqkv + ((size_t)b * T + j) * ld + 2 * a.d + h * DK + hf * 32;
+#pragma unroll
+        for (int k = 0; k < 32; k += 8)
+          *reinterpret_cast<uint4*>(op + k) = make_uint4(
+              pack_bf16(__uint_as_float(dv[k]), __uint_as_float(dv[k + 1])), pack_bf16(__uint_as_float(dv[k + 2]), __uint_as_float(dv[k + 3])),
+              pack_bf16(__uint_as_float(dv[k + 4]), __uint_as_float(dv[k + 5])), pack_bf16(__uint_as_float(dv[k + 6]), __uint_as_float(dv[k + 7])));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
+int launch_relpos_attn_bwd_kv_tc(const AttnArgs& a, const bf16* dctx, const bf16* ws_ds, const bf16* ws_p, const bf16* ws_qu,
+                                 bf16* dqkv, int Tp, cudaStream_t st) {
+  using namespace akv;
+  CUtensorMap tds, tpd, tqu, tdo;
+  {
+    uint64_t dims[3] = {(uint64_t)Tp, (uint64_t)a.T, (uint64_t)a.B * a.H};
+    uint64_t strides[2] = {(uint64_t)Tp * 2, (uint64_t)a.T * Tp * 2};
+    uint32_t box[3] = {64, (uint32_t)BQ, 1}, es[3] = {1, 1, 1};
+    int rc = make_tmap(&tds, ws_ds, 2, 3, dims, strides, box, es, 1);
+    if (rc) return rc;
+    rc = make_tmap(&tpd, ws_p, 2, 3, dims, strides, box, es, 1);
+    if (rc) return rc;
+    uint64_t dd[3] = {(uint64_t)a.d, (uint64_t)a.T, (uint64_t)a.B};
+    uint64_t dstr[2] = {(uint64_t)a.d * 2, (uint64_t)a.T * a.d * 2};
+    uint32_t dbox[3] = {(uint32_t)DK, (uint32_t)BQ, 1};
+    rc = make_tmap(&tqu, ws_qu, 2, 3, dd, dstr, dbox, es, 1);
+    if (rc) return rc;
+    rc = make_tmap(&tdo, dctx, 2, 3, dd, dstr, dbox, es, 1);
+    if (rc) return rc;
+  }
+  static bool set = false;
+  if (!set) {
+    B2C_CUDA(cudaFuncSetAttribute(relpos_attn_bwd_kv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    set = true;
+  }
+  relpos_attn_bwd_kv_tc_kernel<<<dim3((a.T + BK - 1) / BK, a.H, a.B), kThreads, kSmem, st>>>(tds, tpd, tqu, tdo, a, dqkv);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
 }

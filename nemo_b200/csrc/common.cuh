@@ -264,9 +264,20 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
 }
-__device__ __forceinline__ uint32_t dropout_hash(uint64_t seed, uint32_t site, uint64_t pair_idx) {
-  return hash32((uint32_t)pair_idx ^ (uint32_t)seed ^ ((uint32_t)(pair_idx >> 32) * 0x9E3779B1U) ^ (site * 0x85EBCA77U) ^
+// Dropout decisions come in 16-element chunks of the flat element index: one full hash per chunk (`dropout_base`) and
+// one multiply-add + xor-shift per element PAIR (`dropout_word`, two 16-bit lanes compared with the keep threshold).
+// Hot loops that walk aligned chunks pay ~3 integer ops per pair; `dropout_hash(pair_idx)` is the same function for
+// arbitrary indices.
+__device__ __forceinline__ uint32_t dropout_base(uint64_t seed, uint32_t site, uint64_t chunk_idx) {
+  return hash32((uint32_t)chunk_idx ^ (uint32_t)seed ^ ((uint32_t)(chunk_idx >> 32) * 0x9E3779B1U) ^ (site * 0x85EBCA77U) ^
                 __funnelshift_l((uint32_t)(seed >> 32), (uint32_t)(seed >> 32), 13));
+}
+__device__ __forceinline__ uint32_t dropout_word(uint32_t base, uint32_t pair /* 0..7 */) {
+  const uint32_t w = base * (0x9E3779B1U + 0x2545F492U * pair) + pair * 0x632BE5ABU;
+  return w ^ (w >> 15);
+}
+__device__ __forceinline__ uint32_t dropout_hash(uint64_t seed, uint32_t site, uint64_t pair_idx) {
+  return dropout_word(dropout_base(seed, site, pair_idx >> 3), (uint32_t)pair_idx & 7u);
 }
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint32_t site, uint64_t idx, uint32_t keep16) {
   const uint32_t h = dropout_hash(seed, site, idx >> 1);

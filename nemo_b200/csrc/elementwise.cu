@@ -131,7 +131,8 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, 
           float n0 = o.x * next_scale, n1 = o.y * next_scale, n2 = o.z * next_scale, n3 = o.w * next_scale;
           if (drop.keep != 0) {
             const uint64_t idx = (uint64_t)row * (uint64_t)d + (uint64_t)c * 4;
-            const uint32_t h0 = dropout_hash(drop.seed, drop.site, idx >> 1), h1 = dropout_hash(drop.seed, drop.site, (idx + 2) >> 1);
+            const uint32_t hb = dropout_base(drop.seed, drop.site, idx >> 4);
+            const uint32_t h0 = dropout_word(hb, ((uint32_t)idx >> 1) & 7u), h1 = dropout_word(hb, (((uint32_t)idx >> 1) & 7u) + 1u);
             n0 = ((h0 & 0xFFFFu) < drop.keep) ? n0 * drop.scale : 0.f;
             n1 = ((h0 >> 16) < drop.keep) ? n1 * drop.scale : 0.f;
             n2 = ((h1 & 0xFFFFu) < drop.keep) ? n2 * drop.scale : 0.f;

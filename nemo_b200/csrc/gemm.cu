@@ -65,16 +65,15 @@ struct SmemLayout {
 // a row (a thread-per-row store would touch 32 rows per instruction).  Ragged N falls back to per-thread stores.
 constexpr int EW = 16;
 
+// idx0 % 16 == 0 (the host requires N % 16 == 0 when dropout is on): one chunk hash, then a multiply-add per pair
 __device__ __forceinline__ void dropout_ew(float (&v)[EW], const b2c_epilogue& e, uint64_t idx0) {
-  // one hash per 4 elements: h and a cheap second word h * odd; 16-bit lanes vs keep threshold
+  static_assert(EW == 16, "one dropout chunk per epilogue chunk");
+  const uint32_t base = dropout_base(e.seed, e.drop_site, idx0 >> 4);
 #pragma unroll
-  for (int j = 0; j < EW; j += 4) {
-    const uint32_t h0 = dropout_hash(e.seed, e.drop_site, (idx0 + j) >> 1);
-    const uint32_t h1 = dropout_hash(e.seed, e.drop_site, (idx0 + j + 2) >> 1);
-    v[j] = ((h0 & 0xFFFFu) < e.drop_keep) ? v[j] * e.drop_scale : 0.f;
-    v[j + 1] = ((h0 >> 16) < e.drop_keep) ? v[j + 1] * e.drop_scale : 0.f;
-    v[j + 2] = ((h1 & 0xFFFFu) < e.drop_keep) ? v[j + 2] * e.drop_scale : 0.f;
-    v[j + 3] = ((h1 >> 16) < e.drop_keep) ? v[j + 3] * e.drop_scale : 0.f;
+  for (int j = 0; j < EW; j += 2) {
+    const uint32_t h = dropout_word(base, j >> 1);
+    v[j] = ((h & 0xFFFFu) < e.drop_keep) ? v[j] * e.drop_scale : 0.f;
+    v[j + 1] = ((h >> 16) < e.drop_keep) ? v[j + 1] * e.drop_scale : 0.f;
   }
 }
 __device__ __forceinline__ void load_bf16_ew(const bf16* p, float (&v)[EW]) {
@@ -683,6 +682,7 @@ int gemm(const void* A, const void* B, int M, int N, int K, int lda, int ldb, in
          const b2c_epilogue* epi, cudaStream_t stream) {
   B2C_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: bad shape %d %d %d", M, N, K);
   B2C_REQUIRE(epi && epi->out0, "gemm: epilogue output missing");
+  B2C_REQUIRE(epi->drop_keep == 0 || N % 16 == 0, "gemm: dropout epilogues need N %% 16 == 0 (N = %d)", N);
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K; p.splits = 1; p.k_per_split = 0; p.epi = *epi;
