@@ -611,81 +611,136 @@ relpos_attn_bwd_pos_kernel(const AttnArgs a, const bf16* __restrict__ ws_ds, flo
                            int b_per_cta) {
   constexpr int P = DK + 8;
   constexpr int PX = 64 + 8;
+  constexpr int QV = 64 * DK / 8 / 128;  // 16-byte chunks of the q tile per thread
   extern __shared__ __align__(16) uint8_t smraw[];
   bf16* sQ = reinterpret_cast<bf16*>(smraw);  // [64 i][DK] bf16(q+v)
   bf16* sX = sQ + 64 * P;                     // [64 i][64 r]  diagonal gather of dS
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
   const int r0 = blockIdx.x * 64, h = blockIdx.y;
   const int T = a.T, ld = 3 * a.d, R = 2 * T - 1;
-  const float* bv = a.bias_v + h * DK;
   float acc[DK / 8][4];
 #pragma unroll
   for (int nt = 0; nt < DK / 8; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
   // rows i that can pair with r in [r0, r0+64): j = i - (T-1) + r in [0, T)  →  i in [T-1-r0-63, 2T-2-r0]
   const int i_lo = max(0, T - 1 - (r0 + 63)), i_hi = min(T - 1, 2 * T - 2 - r0);
+  const int i_first = (i_lo / 64) * 64;
   const int b_lo = blockIdx.z * b_per_cta, b_hi = min(a.B, b_lo + b_per_cta);
-  for (int b = b_lo; b < b_hi; ++b) {
-    const int len = a.lengths ? min(a.lengths[b], T) : T;
-    const int hi = min(i_hi, len - 1);
-    const bf16* qb = a.qkv + (size_t)b * T * ld + h * DK;
-    const bf16* wds = ws_ds + ((size_t)(b * a.H + h) * T) * Tp;
-    for (int i0 = (i_lo / 64) * 64; i0 <= hi; i0 += 64) {
-      __syncthreads();
-      for (int idx = tid; idx < 64 * (DK / 2); idx += 128) {
-        const int r = idx / (DK / 2), cp = idx - r * (DK / 2);
-        uint32_t val = 0u;
-        if (i0 + r < T) {
-          float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(qb + (size_t)(i0 + r) * ld + cp * 2));
-          val = pack_bf16(v.x + bv[cp * 2], v.y + bv[cp * 2 + 1]);
-        }
-        *reinterpret_cast<uint32_t*>(sQ + r * P + cp * 2) = val;
+  // this thread's slice of the two tiles: q chunk column (fixed) and the gather row / half
+  const int qck = tid & (DK / 8 - 1);
+  float bvr[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) bvr[k] = a.bias_v[h * DK + qck * 8 + k];
+  const int il = tid >> 1, half = tid & 1;
+
+  // The (batch, 64-row block) iterations are software-pipelined: the global loads of step n+1 (q rows as 16-byte
+  // chunks; the diagonal of dS as five ALIGNED 16-byte loads per thread, realigned in registers by a word barrel
+  // shift + half-word funnel shift) are in flight while the tensor cores work on step n.
+  struct Step { int b, i0, hi; };
+  auto first_step = [&](int b) -> Step {
+    Step st{b, i_first, -1};
+    while (st.b < b_hi) {
+      const int len = a.lengths ? min(a.lengths[st.b], T) : T;
+      st.hi = min(i_hi, len - 1);
+      if (st.i0 <= st.hi) return st;
+      ++st.b;
+    }
+    return st;
+  };
+  auto next_step = [&](Step st) -> Step {
+    st.i0 += 64;
+    if (st.i0 <= st.hi) return st;
+    return first_step(st.b + 1);
+  };
+  uint4 qreg[QV];
+  uint4 greg[5];
+  int gmode = 0;  // 0 zeros, 1 aligned fast path (shift = gsh), 2 edge row (element-wise at store time)
+  int gsh = 0;
+  auto prefetch = [&](const Step& st) {
+    const bf16* qb = a.qkv + (size_t)st.b * T * ld + h * DK;
+#pragma unroll
+    for (int k = 0; k < QV; ++k) {
+      const int r = (tid + 128 * k) / (DK / 8);
+      qreg[k] = make_uint4(0, 0, 0, 0);
+      if (st.i0 + r < T) qreg[k] = *reinterpret_cast<const uint4*>(qb + (size_t)(st.i0 + r) * ld + qck * 8);
+    }
+    const int i = st.i0 + il;
+    const int js = i - (T - 1) + r0 + half * 32;
+    if (i > st.hi) {
+      gmode = 0;
+    } else if (js >= 0 && js + 32 <= Tp) {  // columns [T, Tp) of the staged dS are zeros
+      gmode = 1;
+      gsh = js & 7;
+      const uint4* src = reinterpret_cast<const uint4*>(ws_ds + ((size_t)(st.b * a.H + h) * T + i) * Tp + (js & ~7));
+#pragma unroll
+      for (int k = 0; k < 5; ++k) greg[k] = __ldg(src + k);
+    } else {
+      gmode = 2;
+    }
+  };
+  auto publish = [&](const Step& st) {
+#pragma unroll
+    for (int k = 0; k < QV; ++k) {
+      const int r = (tid + 128 * k) / (DK / 8);
+      const uint32_t w[4] = {qreg[k].x, qreg[k].y, qreg[k].z, qreg[k].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16(w[e]);
+        o[e] = (st.i0 + r < T) ? pack_bf16(f.x + bvr[2 * e], f.y + bvr[2 * e + 1]) : 0u;
       }
-      {
-        // diagonal gather: row il of the tile holds dS[i, j] for j = i-(T-1)+r0 .. +63; each thread moves 32 of them
-        const int il = tid >> 1, half = tid & 1;
-        const int i = i0 + il;
-        const int js = i - (T - 1) + r0 + half * 32;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(sX + il * PX + half * 32);
-        if (i > hi) {
+      *reinterpret_cast<uint4*>(sQ + r * P + qck * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(sX + il * PX + half * 32);
+    if (gmode == 1) {
+      uint32_t w[21];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) dst[k] = 0u;
-        } else if (js >= 0 && js + 32 <= Tp) {  // columns [T, Tp) of the staged dS are zeros
-          const bf16* src = wds + (size_t)i * Tp + js;
-          if ((js & 1) == 0) {
+      for (int k = 0; k < 5; ++k) { w[4 * k] = greg[k].x; w[4 * k + 1] = greg[k].y; w[4 * k + 2] = greg[k].z; w[4 * k + 3] = greg[k].w; }
+      w[20] = 0u;
+      const uint32_t wsft = (uint32_t)gsh >> 1, odd16 = (uint32_t)(gsh & 1) * 16u;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) dst[k] = reinterpret_cast<const uint32_t*>(src)[k];
-          } else {
-            const uint32_t* w = reinterpret_cast<const uint32_t*>(src - 1);
-            uint32_t prev = w[0];
+      for (int k = 0; k < 18; ++k) w[k] = (wsft & 2u) ? w[k + 2] : w[k];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) {
-              const uint32_t nxt = (k < 15) ? w[k + 1] : (uint32_t)reinterpret_cast<const uint16_t*>(src)[31];
-              dst[k] = __funnelshift_r(prev, nxt, 16);
-              prev = nxt;
-            }
-          }
-        } else {
-          bf16* d16 = reinterpret_cast<bf16*>(dst);
-          for (int k = 0; k < 32; ++k) {
-            const int j = js + k;
-            d16[k] = (j >= 0 && j < T) ? wds[(size_t)i * Tp + j] : __float2bfloat16_rn(0.f);
-          }
-        }
-      }
-      __syncthreads();
+      for (int k = 0; k < 17; ++k) w[k] = (wsft & 1u) ? w[k + 1] : w[k];
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        uint32_t ax[4];
-        const int mi = lane >> 3;
-        ldsm_x4_trans(ax, sX + (ks * 16 + (mi >> 1) * 8 + (lane & 7)) * PX + warp * 16 + (mi & 1) * 8);
+      for (int k = 0; k < 16; ++k) w[k] = __funnelshift_r(w[k], w[k + 1], odd16);
 #pragma unroll
-        for (int nt = 0; nt < DK / 8; ++nt) {
-          uint32_t b0, b1;
-          ldsm_x2_trans(b0, b1, sQ + (ks * 16 + (lane & 15)) * P + nt * 8);
-          mma16816(acc[nt], ax, b0, b1);
-        }
+      for (int k = 0; k < 4; ++k) dst[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
+    } else if (gmode == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) dst[k] = make_uint4(0, 0, 0, 0);
+    } else {
+      const int i = st.i0 + il;
+      const int js = i - (T - 1) + r0 + half * 32;
+      const bf16* wrow = ws_ds + ((size_t)(st.b * a.H + h) * T + i) * Tp;
+      bf16* d16 = reinterpret_cast<bf16*>(dst);
+      for (int k = 0; k < 32; ++k) {
+        const int j = js + k;
+        d16[k] = (j >= 0 && j < T) ? wrow[j] : __float2bfloat16_rn(0.f);
       }
     }
+  };
+
+  Step cur = first_step(b_lo);
+  if (cur.b < b_hi) prefetch(cur);
+  while (cur.b < b_hi) {
+    __syncthreads();  // the previous step's MMAs have read the tiles
+    publish(cur);
+    const Step nxt = next_step(cur);
+    if (nxt.b < b_hi) prefetch(nxt);
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t ax[4];
+      const int mi = lane >> 3;
+      ldsm_x4_trans(ax, sX + (ks * 16 + (mi >> 1) * 8 + (lane & 7)) * PX + warp * 16 + (mi & 1) * 8);
+#pragma unroll
+      for (int nt = 0; nt < DK / 8; ++nt) {
+        uint32_t b0, b1;
+        ldsm_x2_trans(b0, b1, sQ + (ks * 16 + (lane & 15)) * P + nt * 8);
+        mma16816(acc[nt], ax, b0, b1);
+      }
+    }
+    cur = nxt;
   }
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr) {

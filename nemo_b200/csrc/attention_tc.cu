@@ -34,6 +34,24 @@ constexpr uint32_t kTmemS = 0, kTmemR = 64, kTmemO = 256;  // column offsets
 }  // namespace atc
 
 // 64 columns of fp32 for 32 lanes
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 2^x, single MUFU (exp2f() adds a denormal-range rescale: 3 more instructions per element)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
@@ -55,7 +73,7 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
 
 // write 8 bf16 (one 16-byte chunk `chunk` of row `row`) into a [rows x 64] K-major tile with the 128 B UMMA swizzle
 __device__ __forceinline__ void st_sw128(uint8_t* tile, int row, int chunk, uint4 v) {
-  *reinterpret_cast<uint4*>(tile + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
+  sts128(smem_u32(tile) + row * 128 + ((chunk ^ (row & 7)) << 4), v);
 }
 
 __global__ void __launch_bounds__(atc::kThreads, 1)
@@ -181,7 +199,7 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k)
           umma_bf16(tmem_base + kTmemO, umma_desc_sw128(s_pr + k * 32, 16, 1024), umma_desc_sw128(sv + k * 2048, 64 * BKV * 2, 1024),
-                    idesc_o, k > 0 ? 1u : 0u);
+                    idesc_o, (jt > 0 || k > 0) ? 1u : 0u);
         umma_commit(o_full);
         umma_commit(&empty_bar[stage]);  // K / P-band (consumed by SR_j) and V (by PV_j) of this stage are free
         stage = nstage;
@@ -200,17 +218,19 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
     const float sc2 = a.scale * kLog2e;
     const uint64_t rbase = attn_row_base(a, b, h, row);
     float* xch = reinterpret_cast<float*>(smem + kOffMax);  // [2][128]
-    float o[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) o[k] = 0.f;
-    float m_run = -1e30f, l_run = 0.f;
+    // Online softmax in the exp2 domain on the raw scores v = S + R: p = 2^(v*sc2 - m).  O accumulates in TMEM across
+    // the key tiles; the reference maximum m is only moved (and O / l rescaled) when the running maximum has grown by
+    // more than 2^8 since it was set, so most tiles touch neither O nor the o_full barrier.  The dropout scale 1/(1-p)
+    // is applied once, with the final 1/l.
+    float m_ref = -1e30f, l_run = 0.f;
     uint8_t* prob = smem + kOffProb;
+    const uint32_t keep_hi = a.drop_keep << 16;  // 16-bit lanes of the hash word compared in place
 
     for (int jt = 0; jt < n_kv; ++jt) {
       const int j0 = jt * BKV + half * 32;
       mbar_wait(sr_full, jt & 1);
       tc_fence_after();
-      float s[32];
+      float v[32];
       {
         uint32_t sa[32], x[64];
         tmem_ld32(tlane + kTmemS + half * 32, sa);
@@ -231,31 +251,39 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
 #pragma unroll
         for (int k = 0; k < 32; ++k) x[k] = (sh & 1) ? x[k + 1] : x[k];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float v = (__uint_as_float(sa[k]) + __uint_as_float(x[k])) * sc2;
-          s[k] = (rvalid && j0 + k < len) ? v : -1e30f;
-        }
+        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(sa[k]) + __uint_as_float(x[k]);
       }
-      float mx = -1e30f;
+      if (jt * BKV + BKV > len) {  // ragged last tile (CTA-uniform): keys beyond the length get probability 0
 #pragma unroll
-      for (int k = 0; k < 32; ++k) mx = fmaxf(mx, s[k]);
+        for (int k = 0; k < 32; ++k) v[k] = (j0 + k < len) ? v[k] : -1e30f;
+      }
+      float mx = v[0];
+#pragma unroll
+      for (int k = 1; k < 32; ++k) mx = fmaxf(mx, v[k]);
       // row max across the two column halves: smem exchange + named barrier of the quarter's two warps
       xch[half * 128 + il] = mx;
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-      mx = fmaxf(mx, xch[(half ^ 1) * 128 + il]);
-      const float m_new = fmaxf(m_run, mx);
-      const float corr = exp2f(m_run - m_new);
-      // O_{j-1} (computed against the previous running max) joins the register accumulator, then everything is rescaled
-      if (jt > 0) {
+      mx = fmaxf(mx, xch[(half ^ 1) * 128 + il]) * sc2;
+      if (jt == 0) {
+        m_ref = mx;
+      } else if (__any_sync(0xffffffffu, mx > m_ref + 8.f)) {
+        // move the reference maximum of the rows that need it: O (TMEM, complete up to tile j-1) and l are rescaled
+        const float m_new = (mx > m_ref + 8.f) ? mx : m_ref;
+        const float corr = ex2_approx(m_ref - m_new);
+        m_ref = m_new;
+        l_run *= corr;
         mbar_wait(o_full, (jt - 1) & 1);
         tc_fence_after();
         uint32_t ot[32];
         tmem_ld32(tlane + kTmemO + half * 32, ot);
         tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; ++k) o[k] = (o[k] + __uint_as_float(ot[k])) * corr;
+        for (int k = 0; k < 32; ++k) ot[k] = __float_as_uint(__uint_as_float(ot[k]) * corr);
+        tmem_st32(tlane + kTmemO + half * 32, ot);
+        tmem_st_wait();
       }
-      m_run = m_new;
+      // the P tile is rewritten below: PV_{j-1}, which reads it, must have retired (it has, long ago, in steady state)
+      if (jt > 0) mbar_wait(o_full, (jt - 1) & 1);
       float rs = 0.f;
       uint32_t kbase = 0;
 #pragma unroll
@@ -263,8 +291,7 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
         float p[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float sv = s[c * 8 + k];
-          p[k] = (sv > -1e29f) ? exp2f(sv - m_new) : 0.f;
+          p[k] = ex2_approx(fmaf(v[c * 8 + k], sc2, -m_ref));
           rs += p[k];
         }
         if (a.drop_keep != 0) {
@@ -272,20 +299,23 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
 #pragma unroll
           for (int k = 0; k < 8; k += 2) {
             const uint32_t hw = dropout_word(kbase, (c & 1) * 4 + (k >> 1));
-            p[k] = ((hw & 0xFFFFu) < a.drop_keep) ? p[k] * a.drop_scale : 0.f;
-            p[k + 1] = ((hw >> 16) < a.drop_keep) ? p[k + 1] * a.drop_scale : 0.f;
+            p[k] = ((hw << 16) < keep_hi) ? p[k] : 0.f;
+            p[k + 1] = (hw < keep_hi) ? p[k + 1] : 0.f;
           }
         }
         st_sw128(prob, il, half * 4 + c,
                  make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7])));
       }
-      l_run = l_run * corr + rs;
+      l_run += rs;
       fence_proxy_async();
       tc_fence_before();
       // second barrier of the pair: both halves have read this tile's exchange slots before either overwrites them
       asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
       if (lane == 0) mbar_arrive(p_ready);
     }
+    float o[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) o[k] = 0.f;
     if (n_kv > 0) {
       mbar_wait(o_full, (n_kv - 1) & 1);
       tc_fence_after();
@@ -293,14 +323,14 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       tmem_ld32(tlane + kTmemO + half * 32, ot);
       tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 32; ++k) o[k] += __uint_as_float(ot[k]);
+      for (int k = 0; k < 32; ++k) o[k] = __uint_as_float(ot[k]);
     }
-    // total row sum = sum of the two halves (same running max)
+    // total row sum = sum of the two halves (same reference maximum)
     xch[half * 128 + il] = l_run;
     asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
     const float l_tot = l_run + xch[(half ^ 1) * 128 + il];
     if (row < T) {
-      const float inv = (rvalid && l_tot > 0.f) ? 1.f / l_tot : 0.f;  // fully-masked query rows output exactly 0
+      const float inv = (rvalid && l_tot > 0.f) ? a.drop_scale / l_tot : 0.f;  // fully-masked query rows output exactly 0
       bf16* op = ctx + ((size_t)b * T + row) * a.d + h * DK + half * 32;
 #pragma unroll
       for (int k = 0; k < 32; k += 8)
@@ -313,7 +343,7 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
         for (int k = 0; k < 32; k += 4)
           *reinterpret_cast<float4*>(o32 + k) = make_float4(o[k] * inv, o[k + 1] * inv, o[k + 2] * inv, o[k + 3] * inv);
       }
-      if (lse_out && half == 0) lse_out[((size_t)b * a.H + h) * T + row] = (rvalid && l_tot > 0.f) ? m_run + log2f(l_tot) : 0.f;
+      if (lse_out && half == 0) lse_out[((size_t)b * a.H + h) * T + row] = (rvalid && l_tot > 0.f) ? m_ref + log2f(l_tot) : 0.f;
     }
   }
   tc_fence_before();
@@ -438,6 +468,28 @@ relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
     }
     for (int i = threadIdx.x; i < 3 * kTile / 16; i += blockDim.x)
       reinterpret_cast<uint4*>(smem + kOffDSU)[i] = make_uint4(0, 0, 0, 0);
+    // delta_i = sum_d dO[i,d] * O[i,d] (fp32 O when available): 16 threads per row, 4 columns each, shuffle-reduced
+    float* dl = reinterpret_cast<float*>(smem + kOffXch);
+    for (int idx = threadIdx.x; idx < BQ * 16; idx += blockDim.x) {  // blockDim % 16 == 0: a row never straddles warps
+      const int r = idx >> 4, c4 = (idx & 15) * 4;
+      float acc = 0.f;
+      if (i0 + r < T) {
+        const size_t off = ((size_t)b * T + i0 + r) * a.d + h * DK + c4;
+        const uint2 dy = *reinterpret_cast<const uint2*>(dctx + off);
+        const float2 y0 = unpack_bf16(dy.x), y1 = unpack_bf16(dy.y);
+        if (ctx32) {
+          const float4 o = *reinterpret_cast<const float4*>(ctx32 + off);
+          acc = o.x * y0.x + o.y * y0.y + o.z * y1.x + o.w * y1.y;
+        } else {
+          const uint2 ox = *reinterpret_cast<const uint2*>(ctx + off);
+          const float2 o0 = unpack_bf16(ox.x), o1 = unpack_bf16(ox.y);
+          acc = o0.x * y0.x + o0.y * y0.y + o1.x * y1.x + o1.y * y1.y;
+        }
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if ((idx & 15) == 0) dl[r] = acc;
+    }
   }
   fence_proxy_async();
   tc_fence_before();
@@ -520,31 +572,11 @@ relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
     const float sc2 = a.scale * kLog2e;
     const uint64_t rbase = attn_row_base(a, b, h, row);
     float* xch = reinterpret_cast<float*>(smem + kOffXch);
-    // delta_i = sum_d dO[i,d] * O[i,d] (fp32 O when available) — each half sums its 32 columns, then exchange
-    float dpart = 0.f, lse2 = 0.f;
-    if (row < T) {
-      const bf16* dp = dctx + ((size_t)b * T + row) * a.d + h * DK + half * 32;
-      if (ctx32) {
-        const float* o32 = ctx32 + ((size_t)b * T + row) * a.d + h * DK + half * 32;
-#pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          const float2 y = unpack_bf16(*reinterpret_cast<const uint32_t*>(dp + k));
-          dpart += o32[k] * y.x + o32[k + 1] * y.y;
-        }
-      } else {
-        const bf16* op = ctx + ((size_t)b * T + row) * a.d + h * DK + half * 32;
-#pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(op + k));
-          const float2 y = unpack_bf16(*reinterpret_cast<const uint32_t*>(dp + k));
-          dpart += x.x * y.x + x.y * y.y;
-        }
-      }
-      lse2 = lse[((size_t)b * a.H + h) * T + row];
-    }
-    xch[half * 128 + il] = dpart;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-    const float delta = dpart + xch[(half ^ 1) * 128 + il];
+    // delta_i = sum_d dO[i,d] * O[i,d] was put into xch[] by the whole CTA before the role split (coalesced loads)
+    const float delta = xch[il];
+    float lse2 = 1e30f;  // padded query rows: p = 0
+    if (rvalid) lse2 = lse[((size_t)b * a.H + h) * T + row];
+    const uint32_t keep_hi = a.drop_keep << 16;  // 16-bit lanes of the hash word compared in place
     bf16* wds = ws_ds + ((size_t)(b * a.H + h) * T) * Tp;
     bf16* wp = ws_p + ((size_t)(b * a.H + h) * T) * Tp;
     uint8_t* s_ds = smem + kOffDS;
@@ -574,25 +606,27 @@ relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
         for (int k = 0; k < 34; ++k) x[k] = (sh & 2) ? x[k + 2] : x[k];
 #pragma unroll
         for (int k = 0; k < 32; ++k) x[k] = (sh & 1) ? x[k + 1] : x[k];
-#pragma unroll
+        // p = 2^((S+R)*sc2 - lse) (lse = +huge for padded query rows → 0; padded keys of the ragged last tile → 0),
+        // pd = dropout(p), ds = p * (dropout(dP) - delta) / sqrt(dk)
+        const bool ragged = jt * BKV + BKV > len;  // CTA-uniform
         uint32_t kbase = 0;
 #pragma unroll
         for (int k = 0; k < 32; k += 2) {
-          uint32_t keep = 3u;
+          float km0 = a.drop_scale, km1 = a.drop_scale;
           if (a.drop_keep != 0) {
             if ((k & 15) == 0) kbase = attn_keep_base(a, rbase, j0 + k);
             const uint32_t hw = dropout_word(kbase, (k & 15) >> 1);
-            keep = ((hw & 0xFFFFu) < a.drop_keep ? 1u : 0u) | ((hw >> 16) < a.drop_keep ? 2u : 0u);
+            km0 = ((hw << 16) < keep_hi) ? a.drop_scale : 0.f;
+            km1 = (hw < keep_hi) ? a.drop_scale : 0.f;
           }
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const bool valid = rvalid && (j0 + k + e < len);
-            const float sv = (__uint_as_float(sa[k + e]) + __uint_as_float(x[k + e])) * sc2;
-            const float p = valid ? exp2f(sv - lse2) : 0.f;
-            const bool kp = (keep >> e) & 1u;
-            pd[k + e] = kp ? p * a.drop_scale : 0.f;
-            const float dpe = kp ? __uint_as_float(dpv[k + e]) * a.drop_scale : 0.f;
-            ds[k + e] = p * (dpe - delta) * a.scale;
+            float v = __uint_as_float(sa[k + e]) + __uint_as_float(x[k + e]);
+            if (ragged) v = (j0 + k + e < len) ? v : -1e30f;
+            const float p = ex2_approx(fmaf(v, sc2, -lse2));
+            const float km = e ? km1 : km0;
+            pd[k + e] = p * km;
+            ds[k + e] = (p * a.scale) * fmaf(__uint_as_float(dpv[k + e]), km, -delta);
           }
         }
       }
@@ -637,11 +671,11 @@ relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
         for (int k = 19; k >= 1; --k) e[k] = (wsh & 1u) ? e[k - 1] : e[k];
         if (wsh & 1u) e[0] = 0u;
         const int cid0 = half * 4 + (cbase >> 3) + (sh >> 3);
-        uint4* xq = reinterpret_cast<uint4*>(smem + kOffXch2) + (jt & 1) * 128 + il;
-        if (half == 0) *xq = make_uint4(e[16], e[17], e[18], e[19]);
+        const uint32_t xq = smem_u32(smem + kOffXch2) + (uint32_t)(((jt & 1) * 128 + il) * 16);
+        if (half == 0) sts128(xq, make_uint4(e[16], e[17], e[18], e[19]));
         asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
         if (half == 1) {
-          const uint4 lo = *xq;
+          const uint4 lo = lds128(xq);
           e[0] |= lo.x; e[1] |= lo.y; e[2] |= lo.z; e[3] |= lo.w;
         }
 #pragma unroll

@@ -25,7 +25,7 @@ namespace b2c {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kEpiWarps = 16;
-constexpr int kCluster = 2;  // CTA pair (adjacent M tiles, same N tile): each CTA loads half of the B tile and multicasts it
+constexpr int kCluster = 2;  // CTA pair = one cta_group::2 MMA: 256 x BN tile, each CTA holds its 128 rows of A and BN/2 of B
 constexpr int kNumThreads = 128 + 32 * kEpiWarps;  // 4 role warps + 16 epilogue warps
 
 // Implicit-GEMM geometry of the 3x3 stride-2 subsampling convolution (no im2col is ever materialised: the
@@ -44,15 +44,16 @@ struct GemmParams {
   int M, N, K;
   int splits;       // split-K factor (fp32 atomic accumulate epilogue only); conv wgrad: tap index
   int k_per_split;  // in units of BK blocks
+  int tma_store;    // bf16 outputs leave through TMA stores (tensor maps tmC0 / tmC1) instead of per-thread stores
   b2c_epilogue epi;
   ConvGeom cv;
 };
 
 template <int BN>
 struct SmemLayout {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256) ? 6 : 8;
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (BN / kCluster) * BK * 2;  // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kStages * kStageBytes;
   static constexpr int kStageOut = kBarOffset + 256;                 // per-epilogue-warp 2 KB output staging
@@ -88,20 +89,37 @@ __device__ __forceinline__ void load_bf16_ew(const bf16* p, float (&v)[EW]) {
 __device__ __forceinline__ void stage_store_bf16(uint8_t* stg, int lane, const float (&v)[EW], bf16* out, size_t ldo,
                                                  int m_lane, int M, int n0) {
   __syncwarp();
+  const uint32_t sb = smem_u32(stg);
   const int f = (lane >> 2) & 1;
 #pragma unroll
   for (int k = 0; k < 2; ++k)
-    *reinterpret_cast<uint4*>(stg + lane * 32 + ((k ^ f) << 4)) =
-        make_uint4(pack_bf16(v[8 * k], v[8 * k + 1]), pack_bf16(v[8 * k + 2], v[8 * k + 3]),
-                   pack_bf16(v[8 * k + 4], v[8 * k + 5]), pack_bf16(v[8 * k + 6], v[8 * k + 7]));
+    sts128(sb + lane * 32 + ((k ^ f) << 4),
+           make_uint4(pack_bf16(v[8 * k], v[8 * k + 1]), pack_bf16(v[8 * k + 2], v[8 * k + 3]),
+                      pack_bf16(v[8 * k + 4], v[8 * k + 5]), pack_bf16(v[8 * k + 6], v[8 * k + 7])));
   __syncwarp();
 #pragma unroll
   for (int it = 0; it < 2; ++it) {
     const int row = it * 16 + (lane >> 1), ck = lane & 1;
     const int m = __shfl_sync(0xffffffffu, m_lane, row);
-    const uint4 q = *reinterpret_cast<const uint4*>(stg + row * 32 + ((ck ^ ((row >> 2) & 1)) << 4));
+    const uint4 q = lds128(sb + row * 32 + ((ck ^ ((row >> 2) & 1)) << 4));
     if (m < M) *reinterpret_cast<uint4*>(out + (size_t)m * ldo + n0 + ck * 8) = q;
   }
+}
+// same chunk through a TMA store: the 32 x 16 tile is written in the 32-byte-swizzle layout the tensor map expects
+// (16-byte unit k of row r at r*32 + ((k ^ ((r >> 2) & 1)) << 4)), one lane issues the bulk store of the box whose first
+// row is m_warp; rows >= M and columns >= N are clipped by the tensor map.  The caller has made sure `buf` is free.
+__device__ __forceinline__ void stage_tma_bf16(uint8_t* buf, int lane, const float (&v)[EW], const CUtensorMap* tm, int m_warp,
+                                               int n0) {
+  const uint32_t sb = smem_u32(buf);
+  const int f = (lane >> 2) & 1;
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    sts128(sb + lane * 32 + ((k ^ f) << 4),
+           make_uint4(pack_bf16(v[8 * k], v[8 * k + 1]), pack_bf16(v[8 * k + 2], v[8 * k + 3]),
+                      pack_bf16(v[8 * k + 4], v[8 * k + 5]), pack_bf16(v[8 * k + 6], v[8 * k + 7])));
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) tma_store_2d(tm, buf, n0, m_warp);
 }
 // fp32 chunk (32 rows x 16 cols = 64 B per row): out = residual + v, 8 rows x 64 B per store instruction.
 // The residual (aux) tile is fetched by resid_prefetch() BEFORE the epilogue maths so its latency is hidden.
@@ -121,18 +139,21 @@ __device__ __forceinline__ void resid_prefetch(ResidTile& t, const float* aux, s
 __device__ __forceinline__ void stage_store_f32(uint8_t* stg, int lane, const float (&v)[EW], float* out, const ResidTile& t,
                                                 size_t ldo, int M, int n0) {
   __syncwarp();
+  const uint32_t sb = smem_u32(stg);
   const int f = (lane >> 1) & 3;
 #pragma unroll
   for (int k = 0; k < 4; ++k)
-    *reinterpret_cast<float4*>(stg + lane * 64 + ((k ^ f) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    sts128(sb + lane * 64 + ((k ^ f) << 4), make_uint4(__float_as_uint(v[4 * k]), __float_as_uint(v[4 * k + 1]),
+                                                       __float_as_uint(v[4 * k + 2]), __float_as_uint(v[4 * k + 3])));
   __syncwarp();
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int row = it * 8 + (lane >> 2), ck = lane & 3;
-    const float4 q = *reinterpret_cast<const float4*>(stg + row * 64 + ((ck ^ ((row >> 1) & 3)) << 4));
+    const uint4 q = lds128(sb + row * 64 + ((ck ^ ((row >> 1) & 3)) << 4));
     if (t.mm[it] < M)
       *reinterpret_cast<float4*>(out + (size_t)t.mm[it] * ldo + n0 + ck * 4) =
-          make_float4(q.x + t.r[it].x, q.y + t.r[it].y, q.z + t.r[it].z, q.w + t.r[it].w);
+          make_float4(__uint_as_float(q.x) + t.r[it].x, __uint_as_float(q.y) + t.r[it].y, __uint_as_float(q.z) + t.r[it].z,
+                      __uint_as_float(q.w) + t.r[it].w);
   }
 }
 
@@ -221,6 +242,30 @@ __device__ __forceinline__ void epilogue_row(const b2c_epilogue& e, int m, int n
 
 // Warp-collective epilogue of one 32-row x EW-column chunk.
 // bf16 side input (z for SiLU', y for ReLU') of one row chunk, fetched one chunk ahead of its use
+// bf16 outputs of the plain GEMMs leave through TMA stores: per epilogue warp two 1 KB staging buffers; `turn`
+// alternates them for single-output modes, the SiLU mode (two outputs) uses both for every chunk
+struct TmaOut {
+  const CUtensorMap* tm0;
+  const CUtensorMap* tm1;
+  int m_warp;  // first accumulator row of this warp's 32 rows
+  int on;
+  int turn;
+};
+template <int MODE>
+constexpr bool kTmaStoreMode = (MODE == B2C_EPI_BF16 || MODE == B2C_EPI_SILU || MODE == B2C_EPI_GLU_MASK || MODE == B2C_EPI_DSILU ||
+                                MODE == B2C_EPI_RELU_MASK || MODE == B2C_EPI_RELU_BWD);
+// out0 chunk: TMA path (waits until the staging buffer it is about to overwrite has been read) or per-thread stores
+__device__ __forceinline__ void store_out0_bf16(uint8_t* stg, int lane, const float (&v)[EW], bf16* out, size_t ldo, int m, int M,
+                                                int n0, bool ts, const TmaOut& to) {
+  if (ts) {
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+    stage_tma_bf16(stg + (to.turn & 1) * 1024, lane, v, to.tm0, to.m_warp, n0);
+    if (lane == 0) bulk_commit();
+  } else {
+    stage_store_bf16(stg, lane, v, out, ldo, m, M, n0);
+  }
+}
 struct AuxChunk {
   uint4 q[2];
 };
@@ -244,12 +289,14 @@ __device__ __forceinline__ void unpack_aux(const AuxChunk& a, float (&v)[EW]) {
 
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int n0, int M, int N, const uint32_t (&acc)[EW],
-                                               const AuxChunk& auxc, bool atomic, uint8_t* stg, int lane) {
+                                               const AuxChunk& auxc, bool atomic, uint8_t* stg, int lane, const TmaOut& to) {
   if (n0 >= N) return;  // warp-uniform
   float v[EW];
 #pragma unroll
   for (int j = 0; j < EW; ++j) v[j] = __uint_as_float(acc[j]);
-  if (MODE == B2C_EPI_ACCUM_F32 || n0 + EW > N) {
+  // TMA-stored outputs: ragged rows / columns are clipped by the tensor map, no per-thread fallback needed
+  const bool ts = kTmaStoreMode<MODE> && to.on;
+  if (MODE == B2C_EPI_ACCUM_F32 || ((!ts || MODE == B2C_EPI_GLU_MASK) && n0 + EW > N)) {
     epilogue_row<MODE>(e, m, n0, M, N, v, atomic);
     return;
   }
@@ -273,7 +320,7 @@ __device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int
     valid = t < e.lengths[b];
   }
   if (MODE == B2C_EPI_BF16) {
-    stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
+    store_out0_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0, ts, to);
   } else if (MODE == B2C_EPI_SILU) {
     // z = bf16(acc+bias) → out0 ; h = bf16(dropout(silu(z))) → out1   (conformer_modules.py:383-385)
     float h[EW];
@@ -287,8 +334,16 @@ __device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int
       for (int j = 0; j < EW; ++j) h[j] = bf16_round(h[j]);
       dropout_ew(h, e, didx);
     }
-    stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
-    stage_store_bf16(stg, lane, h, reinterpret_cast<bf16*>(e.out1), ldo, m, M, n0);
+    if (ts) {
+      if (lane == 0) bulk_wait_read<0>();
+      __syncwarp();
+      stage_tma_bf16(stg, lane, v, to.tm0, to.m_warp, n0);
+      stage_tma_bf16(stg + 1024, lane, h, to.tm1, to.m_warp, n0);
+      if (lane == 0) bulk_commit();
+    } else {
+      stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
+      stage_store_bf16(stg, lane, h, reinterpret_cast<bf16*>(e.out1), ldo, m, M, n0);
+    }
   } else if (MODE == B2C_EPI_RESID_F32) {
     // out0_f32 = (aux_f32 ? aux : 0) + alpha * dropout(bf16(acc+bias))
 #pragma unroll
@@ -306,7 +361,7 @@ __device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int
       v[j + 1] = bf16_round(v[j + 1]);
       u[j >> 1] = valid ? v[j] * sigmoid_f(v[j + 1]) : 0.f;
     }
-    stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
+    store_out0_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0, ts, to);
     if (rowok)
       *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(e.out1) + (size_t)m * (ldo >> 1) + (n0 >> 1)) =
           make_uint4(pack_bf16(u[0], u[1]), pack_bf16(u[2], u[3]), pack_bf16(u[4], u[5]), pack_bf16(u[6], u[7]));
@@ -319,17 +374,17 @@ __device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int
     if (e.drop_keep != 0) dropout_ew(v, e, didx);
 #pragma unroll
     for (int j = 0; j < EW; ++j) v[j] *= dsilu_f(zz[j]);
-    stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
+    store_out0_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0, ts, to);
   } else if (MODE == B2C_EPI_RELU_MASK) {
 #pragma unroll
     for (int j = 0; j < EW; ++j) v[j] = valid ? fmaxf(v[j], 0.f) : 0.f;
-    stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
+    store_out0_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0, ts, to);
   } else if (MODE == B2C_EPI_RELU_BWD) {
     float yy[EW];
     unpack_aux(auxc, yy);
 #pragma unroll
     for (int j = 0; j < EW; ++j) v[j] = yy[j] > 0.f ? v[j] : 0.f;
-    stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
+    store_out0_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0, ts, to);
   }
 }
 
@@ -338,7 +393,8 @@ __device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int
 //       3 = conv weight-gradient (tokens are the contraction; A = dY, B = strided gather of X, one tap per `split`)
 template <int BN, int A_MN, int B_MN, int MODE, int CONV = 0>
 __global__ void __launch_bounds__(kNumThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC0, const __grid_constant__ CUtensorMap tmC1, const GemmParams p) {
   using L = SmemLayout<BN>;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -353,8 +409,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m_tiles = (CONV == 1 || CONV == 2) ? p.M : (p.M + BM - 1) / BM;  // conv fwd/dgrad: p.M = #row tiles
   const int n_tiles = (p.N + BN - 1) / BN;
   // Tiles are enumerated so that the two CTAs of a cluster (blockIdx.x = 2c, 2c+1; persistent stride is even) always
-  // work on M-adjacent tiles of the SAME n-tile / split at the same time: they share the B operand tile, each TMA-loads
-  // half of it and multicasts it to both.  An odd tile row count adds one dummy row tile (TMA zero-fills, epilogue skips).
+  // work on M-adjacent tiles of the SAME n-tile / split at the same time: together they form one 256 x BN cta_group::2
+  // tile.  Each CTA TMA-loads its own 128 rows of A and its half of the B tile into its own shared memory, the leader
+  // (even) CTA issues the MMAs for both, each CTA's TMEM receives its 128 accumulator rows and each runs its own
+  // epilogue.  An odd tile row count adds one dummy row tile (TMA zero-fills, epilogue skips).
   const int m_pairs = (m_tiles + kCluster - 1) / kCluster;
   const int total_tiles = m_pairs * kCluster * n_tiles * p.splits;
   const uint32_t crank = (kCluster > 1) ? cluster_ctarank() : 0u;
@@ -368,7 +426,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int kb_total = (CONV != 0) ? p.K : (p.K + BK - 1) / BK;               // conv: p.K = #k-blocks
   // bytes one stage receives (partial boxes of the conv gathers deliver fewer rows than the slot holds)
   const uint32_t stage_tx = (CONV == 1 || CONV == 2) ? (uint32_t)(p.cv.TR * p.cv.Fq * BK * 2 + L::kBBytes)
-                            : (CONV == 3)            ? (uint32_t)((BM / 64 + BN / 64) * p.cv.TR * p.cv.Fq * 128)
+                            : (CONV == 3)            ? (uint32_t)((BM / 64 + BN / 64 / kCluster) * p.cv.TR * p.cv.Fq * 128)
                                                      : (uint32_t)L::kStageBytes;
   if (CONV == 3) {
     // rows the partial boxes never write must read as zero for the MN-major contraction
@@ -383,95 +441,89 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], kCluster);  // a stage is reusable once BOTH CTAs' MMAs have consumed it
+      mbar_init(&full_bar[i], 1);   // leader only: its own expect_tx; both CTAs' TMA bytes complete on it
+      mbar_init(&empty_bar[i], 1);  // the leader's commit arrives on both CTAs' barriers
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiWarps);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[i], kCluster * kEpiWarps);  // leader only: one arrive per epilogue warp of BOTH CTAs
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<2 * BN>(tmem_slot);
+  if (warp == 2) tmem_alloc_2sm<2 * BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
-  if (kCluster > 1) cluster_sync_all();  // peer barriers are initialised before any multicast / remote arrive
+  cluster_sync_all();  // peer barriers are initialised and its TMEM allocated before any remote arrive / paired MMA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0, phase = 0;
-      constexpr uint16_t kMask = (uint16_t)((1u << kCluster) - 1);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int m_blk, n_blk, split;
         decode(tile, m_blk, n_blk, split);
-        const int m0 = m_blk * BM, n0 = n_blk * BN;
+        const int m0 = m_blk * BM, n0 = n_blk * BN + (int)crank * (BN / kCluster);  // this CTA's half of the B tile
         const int kb0 = (CONV == 3) ? 0 : split * p.k_per_split;
         const int kb1 = (CONV == 3) ? kb_total : min(kb_total, kb0 + p.k_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
-          mbar_expect_tx(&full_bar[stage], stage_tx);
-          // ---- A operand: private to this CTA
+          uint64_t* fb = &full_bar[stage];  // every load below signals the LEADER's barrier at this offset
+          if (crank == 0) mbar_expect_tx(fb, kCluster * stage_tx);
+          // ---- A operand: this CTA's 128 rows
           if (CONV == 1 || CONV == 2) {
             const int cblks = p.cv.C / BK;
             const int tap = kb / cblks, c0 = (kb - tap * cblks) * BK;
             const int bb = m_blk / p.cv.tiles_per_batch, t0 = (m_blk - bb * p.cv.tiles_per_batch) * p.cv.TR;
-            tma_load_4d(sa, &tmA, &full_bar[stage], c0, p.cv.tap_f[tap], t0 * p.cv.a_t_mul + p.cv.tap_t[tap], bb);
+            tma_load_4d_2sm(sa, &tmA, fb, c0, p.cv.tap_f[tap], t0 * p.cv.a_t_mul + p.cv.tap_t[tap], bb);
           } else if (CONV == 3) {
             const int bb = kb / p.cv.tiles_per_batch, t0 = (kb - bb * p.cv.tiles_per_batch) * p.cv.TR;
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_4d(sa + c * (64 * BK * 2), &tmA, &full_bar[stage], m0 + c * 64, 0, t0, bb);
+            for (int c = 0; c < BM / 64; ++c) tma_load_4d_2sm(sa + c * (64 * BK * 2), &tmA, fb, m0 + c * 64, 0, t0, bb);
           } else if (A_MN) {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (64 * BK * 2), &tmA, &full_bar[stage], m0 + c * 64, kb * BK);
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d_2sm(sa + c * (64 * BK * 2), &tmA, fb, m0 + c * 64, kb * BK);
           } else {
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * BK, m0);
+            tma_load_2d_2sm(sa, &tmA, fb, kb * BK, m0);
           }
-          // ---- B operand: this CTA fetches its 1/kCluster share and multicasts it to the whole cluster
+          // ---- B operand: this CTA's BN/2 rows (K-major) or columns (MN-major) of the tile
           if (CONV == 3) {
             const int bb = kb / p.cv.tiles_per_batch, t0 = (kb - bb * p.cv.tiles_per_batch) * p.cv.TR;
             const int tap = split;  // kh*3 + kw
 #pragma unroll
-            for (int c = 0; c < BN / 64 / kCluster; ++c) {
-              const int cc = (int)crank * (BN / 64 / kCluster) + c;
-              tma_load_4d_mc(sb + cc * (64 * BK * 2), &tmB, &full_bar[stage], n0 + cc * 64, tap % 3 - 1, 2 * t0 + tap / 3 - 1, bb, kMask);
-            }
+            for (int c = 0; c < BN / 64 / kCluster; ++c)
+              tma_load_4d_2sm(sb + c * (64 * BK * 2), &tmB, fb, n0 + c * 64, tap % 3 - 1, 2 * t0 + tap / 3 - 1, bb);
           } else if (CONV == 1 || CONV == 2) {
             const int cblks = p.cv.C / BK;
             const int tap = kb / cblks, c0 = (kb - tap * cblks) * BK;
-            tma_load_2d_mc(sb + crank * (BN / kCluster) * (BK * 2), &tmB, &full_bar[stage], p.cv.tap_k[tap] + c0,
-                           n0 + (int)crank * (BN / kCluster), kMask);
+            tma_load_2d_2sm(sb, &tmB, fb, p.cv.tap_k[tap] + c0, n0);
           } else if (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BN / 64 / kCluster; ++c) {
-              const int cc = (int)crank * (BN / 64 / kCluster) + c;
-              tma_load_2d_mc(sb + cc * (64 * BK * 2), &tmB, &full_bar[stage], n0 + cc * 64, kb * BK, kMask);
-            }
+            for (int c = 0; c < BN / 64 / kCluster; ++c) tma_load_2d_2sm(sb + c * (64 * BK * 2), &tmB, fb, n0 + c * 64, kb * BK);
           } else {
-            tma_load_2d_mc(sb + crank * (BN / kCluster) * (BK * 2), &tmB, &full_bar[stage], kb * BK,
-                           n0 + (int)crank * (BN / kCluster), kMask);
+            tma_load_2d_2sm(sb, &tmB, fb, kb * BK, n0);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    if (lane == 0 && crank == 0) {  // the leader CTA issues the pair's MMAs
+      constexpr uint32_t idesc = umma_idesc_bf16(kCluster * BM, BN, A_MN, B_MN);
+      constexpr uint16_t kBoth = (uint16_t)((1u << kCluster) - 1);
       int stage = 0, phase = 0, as = 0, aphase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int m_blk, n_blk, split;
         decode(tile, m_blk, n_blk, split);
         const int kb0 = (CONV == 3) ? 0 : split * p.k_per_split;
         const int kb1 = (CONV == 3) ? kb_total : min(kb_total, kb0 + p.k_per_split);
-        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);  // both CTAs' epilogues have drained this accumulator stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait(&full_bar[stage], phase);    // both CTAs' operand tiles have landed
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
           const uint32_t sb = sa + L::kABytes;
@@ -479,16 +531,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < BK / 16; ++k) {
             // K-major: +32 B per K=16 inside the 128 B swizzle row; SBO = 8 rows * 128 B.
             // MN-major: 16 k-rows * 128 B = 2048 B per K=16; LBO = stride between 64-wide MN chunks (64 k-rows*128 B).
+            // The same descriptors (= shared-memory offsets) are applied in both CTAs.
             const uint64_t da = A_MN ? umma_desc_sw128(sa + k * 2048, 64 * BK * 2, 1024) : umma_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? umma_desc_sw128(sb + k * 2048, 64 * BK * 2, 1024) : umma_desc_sw128(sb + k * 32, 16, 1024);
-            umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_bf16_2sm(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          // frees the smem slot once these MMAs retire — in BOTH CTAs: the peer multicasts into this slot too
-          if (kCluster > 1) umma_commit_mc(&empty_bar[stage], (uint16_t)((1u << kCluster) - 1));
-          else umma_commit(&empty_bar[stage]);
+          umma_commit_2sm(&empty_bar[stage], kBoth);  // frees the smem slot in BOTH CTAs once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete → epilogue
+        umma_commit_2sm(&tfull_bar[as], kBoth);  // accumulator complete → both epilogues
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -496,6 +547,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;             // TMEM lane quarter this warp may access (= warp id % 4)
     const int cgrp = (warp - 4) >> 2;   // four warps share a quarter and split the column chunks
     uint8_t* stg = smem + L::kStageOut + (warp - 4) * 2048;
+    TmaOut to;
+    to.tm0 = &tmC0; to.tm1 = &tmC1; to.on = (CONV == 0) ? p.tma_store : 0; to.turn = 0; to.m_warp = 0;
     int as = 0, aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int m_blk, n_blk, split;
@@ -524,31 +577,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool atomic = (CONV == 0 && p.splits > 1);
       uint32_t acc[2][EW];
       AuxChunk auxc[2];
-      tmem_ld16(trow + (uint32_t)(cgrp * EW), acc[0]);
-      aux_prefetch<MODE>(auxc[0], epi, m, n0 + cgrp * EW, m_bound, p.N);
+      to.m_warp = m0 + q * 32;
+      // each warp owns kChunks CONSECUTIVE 16-column chunks (adjacent chunks of a row leave the SM back to back)
+      tmem_ld16(trow + (uint32_t)(cgrp * kChunks * EW), acc[0]);
+      aux_prefetch<MODE>(auxc[0], epi, m, n0 + cgrp * kChunks * EW, m_bound, p.N);
 #pragma unroll
       for (int i = 0; i < kChunks; ++i) {
-        const int c = cgrp + i * (kEpiWarps / 4);
+        const int c = cgrp * kChunks + i;
         tmem_ld_wait();
         if (i + 1 < kChunks) {
-          const int cn = c + kEpiWarps / 4;
-          tmem_ld16(trow + (uint32_t)(cn * EW), acc[(i + 1) & 1]);
-          aux_prefetch<MODE>(auxc[(i + 1) & 1], epi, m, n0 + cn * EW, m_bound, p.N);
+          tmem_ld16(trow + (uint32_t)((c + 1) * EW), acc[(i + 1) & 1]);
+          aux_prefetch<MODE>(auxc[(i + 1) & 1], epi, m, n0 + (c + 1) * EW, m_bound, p.N);
         }
-        epilogue_chunk<MODE>(epi, m, n0 + c * EW, m_bound, p.N, acc[i & 1], auxc[i & 1], atomic, stg, lane);
+        epilogue_chunk<MODE>(epi, m, n0 + c * EW, m_bound, p.N, acc[i & 1], auxc[i & 1], atomic, stg, lane, to);
+        to.turn ^= 1;
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (kTmaStoreMode<MODE> && to.on && lane == 0) bulk_wait_all();  // shared-memory sources stay valid until read
   }
   tc_fence_before();
   __syncthreads();
-  if (kCluster > 1) cluster_sync_all();  // no CTA may exit while its peer can still multicast into / arrive on its smem
+  cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer's MMAs / arrives can still touch it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<2 * BN>(tmem_base);
+    tmem_dealloc_2sm<2 * BN>(tmem_base);
   }
 }
 
@@ -584,7 +640,11 @@ __global__ void gemm_simt_kernel(const bf16* __restrict__ A, const bf16* __restr
 static int g_gemm_impl = -1;  // 0 = tcgen05, 1 = simt (debug)
 
 template <int BN, int A_MN, int B_MN, int MODE, int CONV = 0>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream,
+                     const CUtensorMap* tc0 = nullptr, const CUtensorMap* tc1 = nullptr) {
+  static const CUtensorMap kNoMap = {};
+  const CUtensorMap& c0 = tc0 ? *tc0 : kNoMap;
+  const CUtensorMap& c1 = tc1 ? *tc1 : (tc0 ? *tc0 : kNoMap);
   using L = SmemLayout<BN>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, MODE, CONV>;
   static bool attr_set = false;
@@ -609,7 +669,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   count_launch();
-  B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, c0, c1, p));
   return B2C_OK;
 }
 
@@ -635,12 +695,22 @@ static int dispatch_mode(const void* A, const void* B, int lda, int ldb, int a_m
   const int BN = (p.N >= 256 && p.N % 256 == 0) ? 256 : 128;
   const int kb_total = (p.K + BK - 1) / BK;
   if (MODE == B2C_EPI_ACCUM_F32) {
-    const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
-    int splits = 1;
-    if (tiles < num_sms()) splits = (num_sms() + tiles - 1) / tiles;
-    if (splits > kb_total) splits = kb_total;
-    if (splits < 1) splits = 1;
-    p.k_per_split = (kb_total + splits - 1) / splits;
+    // split-K so that the (pair-tile x split) work units fill whole waves of CTA pairs: minimise
+    // rounds * (k-blocks per unit + fixed per-unit cost of the atomic epilogue), fewest splits on ties
+    const int pair_tiles = (((p.M + BM - 1) / BM + kCluster - 1) / kCluster) * ((p.N + BN - 1) / BN);
+    const int clusters = num_sms() / kCluster;
+    int best_s = 1;
+    long long best_t = -1;
+    for (int sp = 1; sp <= 64 && sp <= kb_total; ++sp) {
+      const int kper = (kb_total + sp - 1) / sp;
+      if (sp > 1 && kper < 8) break;
+      const int s_eff = (kb_total + kper - 1) / kper;
+      const long long units = (long long)pair_tiles * s_eff;
+      const long long rounds = (units + clusters - 1) / clusters;
+      const long long t = rounds * (kper + 6);
+      if (best_t < 0 || t < best_t) { best_t = t; best_s = s_eff; }
+    }
+    p.k_per_split = (kb_total + best_s - 1) / best_s;
     p.splits = (kb_total + p.k_per_split - 1) / p.k_per_split;
   } else {
     p.splits = 1;
@@ -662,7 +732,25 @@ static int dispatch_mode(const void* A, const void* B, int lda, int ldb, int a_m
     rc = make_tmap(&tb, B, 2, 2, dims, strides, box, es, 1);
     if (rc) return rc;
   }
-#define B2C_GO(BN_, AM_, BM_) return launch_tc<BN_, AM_, BM_, MODE>(ta, tb, p, stream)
+  // bf16 outputs through TMA stores when the output rows are 16-byte aligned (box = one 32-row x 16-column chunk)
+  CUtensorMap tc0, tc1;
+  const CUtensorMap *pc0 = nullptr, *pc1 = nullptr;
+  p.tma_store = 0;
+  if (kTmaStoreMode<MODE> && p.epi.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(p.epi.out0) & 15) == 0 &&
+      (MODE != B2C_EPI_SILU || (p.epi.out1 && (reinterpret_cast<uintptr_t>(p.epi.out1) & 15) == 0))) {
+    uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.M}, strides[1] = {(uint64_t)p.epi.ldo * 2};
+    uint32_t box[2] = {(uint32_t)EW, 32}, es[2] = {1, 1};
+    int rc = make_tmap(&tc0, p.epi.out0, 2, 2, dims, strides, box, es, 3);
+    if (rc) return rc;
+    pc0 = &tc0;
+    if (MODE == B2C_EPI_SILU) {
+      rc = make_tmap(&tc1, p.epi.out1, 2, 2, dims, strides, box, es, 3);
+      if (rc) return rc;
+      pc1 = &tc1;
+    }
+    p.tma_store = 1;
+  }
+#define B2C_GO(BN_, AM_, BM_) return launch_tc<BN_, AM_, BM_, MODE>(ta, tb, p, stream, pc0, pc1)
   if (BN == 256) {
     if (!a_mn && !b_mn) B2C_GO(256, 0, 0);
     if (!a_mn && b_mn) B2C_GO(256, 0, 1);

@@ -53,7 +53,7 @@ static EncodeTiledFn get_encode() {
 }
 
 int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides, int swizzle128) {
+              const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides, int swizzle) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -69,7 +69,7 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int rank, cons
   }
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle == 3 ? CU_TENSOR_MAP_SWIZZLE_32B : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed: %d (rank %d dims %llu %llu box %u %u stride0 %llu)", (int)r, rank,
