@@ -27,8 +27,8 @@ constexpr int kQBytes = BQ * DK * 2;                      // 16 KB each (q+u, q+
 constexpr int kProbBytes = BQ * BKV * 2;                  // 16 KB
 constexpr int kOffQu = 0, kOffQv = kQBytes, kOffProb = 2 * kQBytes, kOffStage = 2 * kQBytes + kProbBytes;
 constexpr int kOffBar = kOffStage + kStages * kStageBytes;
-constexpr int kOffMax = kOffBar + 256;  // float [2][128] row-max / row-sum exchange between the two halves of a row
-constexpr int kSmem = kOffMax + 2 * 128 * 4 + 1024;
+constexpr int kOffMax = kOffBar + 256;  // float [3][2][128] row-max / row-sum exchange between the two halves of a row
+constexpr int kSmem = kOffMax + 3 * 2 * 128 * 4 + 1024;
 constexpr int kThreads = 128 + 8 * 32;
 constexpr uint32_t kTmemS = 0, kTmemR = 64, kTmemO = 256;  // column offsets
 }  // namespace atc
@@ -222,7 +222,7 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
     // the key tiles; the reference maximum m is only moved (and O / l rescaled) when the running maximum has grown by
     // more than 2^8 since it was set, so most tiles touch neither O nor the o_full barrier.  The dropout scale 1/(1-p)
     // is applied once, with the final 1/l.
-    float m_ref = -1e30f, l_run = 0.f;
+    float m_ref = -1e30f, l_run = 0.f, mx_prev = -1e30f;
     uint8_t* prob = smem + kOffProb;
     const uint32_t keep_hi = a.drop_keep << 16;  // 16-bit lanes of the hash word compared in place
 
@@ -260,30 +260,37 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       float mx = v[0];
 #pragma unroll
       for (int k = 1; k < 32; ++k) mx = fmaxf(mx, v[k]);
-      // row max across the two column halves: smem exchange + named barrier of the quarter's two warps
-      xch[half * 128 + il] = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-      mx = fmaxf(mx, xch[(half ^ 1) * 128 + il]) * sc2;
+      mx *= sc2;
+      // Row maximum across the two column halves.  Only tile 0 synchronises the two warps of a quarter; afterwards the
+      // reference follows the row maximum of the PREVIOUS tile (both halves read the same two values, so they always
+      // agree on it): 2^(v - m_ref) may then exceed 2^8 by however much this tile tops the last one — harmless in fp32 /
+      // bf16, and it takes every named barrier out of the steady-state loop.
+      float* slot = xch + (jt % 3) * 256;
+      slot[half * 128 + il] = mx;
       if (jt == 0) {
-        m_ref = mx;
-      } else if (__any_sync(0xffffffffu, mx > m_ref + 8.f)) {
-        // move the reference maximum of the rows that need it: O (TMEM, complete up to tile j-1) and l are rescaled
-        const float m_new = (mx > m_ref + 8.f) ? mx : m_ref;
-        const float corr = ex2_approx(m_ref - m_new);
-        m_ref = m_new;
-        l_run *= corr;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+        m_ref = fmaxf(mx, slot[(half ^ 1) * 128 + il]);
+      } else {
+        // PV_{j-1} has retired: every softmax warp finished tile j-1 (its maximum is visible) and the P tile is free
         mbar_wait(o_full, (jt - 1) & 1);
-        tc_fence_after();
-        uint32_t ot[32];
-        tmem_ld32(tlane + kTmemO + half * 32, ot);
-        tmem_ld_wait();
+        const float seen = fmaxf(mx_prev, xch[((jt - 1) % 3) * 256 + (half ^ 1) * 128 + il]);
+        if (__any_sync(0xffffffffu, seen > m_ref + 8.f)) {
+          // move the reference maximum of the rows that need it: O (TMEM, complete up to tile j-1) and l are rescaled
+          const float m_new = (seen > m_ref + 8.f) ? seen : m_ref;
+          const float corr = ex2_approx(m_ref - m_new);
+          m_ref = m_new;
+          l_run *= corr;
+          tc_fence_after();
+          uint32_t ot[32];
+          tmem_ld32(tlane + kTmemO + half * 32, ot);
+          tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; ++k) ot[k] = __float_as_uint(__uint_as_float(ot[k]) * corr);
-        tmem_st32(tlane + kTmemO + half * 32, ot);
-        tmem_st_wait();
+          for (int k = 0; k < 32; ++k) ot[k] = __float_as_uint(__uint_as_float(ot[k]) * corr);
+          tmem_st32(tlane + kTmemO + half * 32, ot);
+          tmem_st_wait();
+        }
       }
-      // the P tile is rewritten below: PV_{j-1}, which reads it, must have retired (it has, long ago, in steady state)
-      if (jt > 0) mbar_wait(o_full, (jt - 1) & 1);
+      mx_prev = mx;
       float rs = 0.f;
       uint32_t kbase = 0;
 #pragma unroll
@@ -309,8 +316,7 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       l_run += rs;
       fence_proxy_async();
       tc_fence_before();
-      // second barrier of the pair: both halves have read this tile's exchange slots before either overwrites them
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+      __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
     }
     float o[32];
@@ -396,7 +402,8 @@ constexpr int kKBytes = BKV * DK * 2, kVBytes = BKV * DK * 2, kPBytes = BAND * D
 constexpr int kStageBytes = kKBytes + kVBytes + kPBytes;  // 40 KB
 constexpr int kTile = BQ * DK * 2;                        // 16 KB: one [128 x 64] bf16 K-major tile
 constexpr int kOffQu = 0, kOffQv = kTile, kOffDO = 2 * kTile, kOffDS = 3 * kTile, kOffDSU = 4 * kTile;  // dS~: 3 tiles
-constexpr int kOffStage = 7 * kTile;
+constexpr int kOffPD = 7 * kTile;  // P_dropped tile, only staged for the TMA store to the key-side workspace
+constexpr int kOffStage = 8 * kTile;
 constexpr int kOffBar = kOffStage + kStages * kStageBytes;
 constexpr int kOffXch = kOffBar + 256;            // float [2][128]
 constexpr int kOffXch2 = kOffXch + 2 * 128 * 4;   // uint4 [2][128]: half 0 → half 1 boundary chunk of the un-skewed row
@@ -407,7 +414,8 @@ constexpr uint32_t kTmS = 0, kTmR = 64, kTmDP = 256, kTmDQU = 320, kTmDQV = 384;
 
 __global__ void __launch_bounds__(atb::kThreads, 1)
 relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                            const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmDO, const AttnArgs a,
+                            const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmDO,
+                            const __grid_constant__ CUtensorMap tmWS, const __grid_constant__ CUtensorMap tmWP, const AttnArgs a,
                             const float* __restrict__ ctx32, const bf16* __restrict__ ctx, const bf16* __restrict__ dctx,
                             const float* __restrict__ lse, bf16* __restrict__ dqkv, float* __restrict__ dbias_u,
                             float* __restrict__ dbias_v, bf16* __restrict__ ws_ds, bf16* __restrict__ ws_p,
@@ -422,7 +430,8 @@ relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
   uint64_t* ds_ready = srd_free + 1;         // dS / dS~ of the current tile are in shared memory
   uint64_t* dq_done = ds_ready + 1;          // the dQ MMAs that read them have retired
   uint64_t* do_full = dq_done + 1;           // dO tile landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(do_full + 1);
+  uint64_t* st_done = do_full + 1;           // the TMA stores of the dS / P_dropped tiles have read shared memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(st_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -436,7 +445,7 @@ relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(srd_full, 1); mbar_init(srd_free, 8); mbar_init(ds_ready, 8); mbar_init(dq_done, 1); mbar_init(do_full, 1);
+    mbar_init(srd_full, 1); mbar_init(srd_free, 8); mbar_init(ds_ready, 8); mbar_init(dq_done, 1); mbar_init(do_full, 1); mbar_init(st_done, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -563,6 +572,21 @@ relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
         phase = nphase;
       }
     }
+  } else if (warp == 3) {
+    // staging for the key- and position-side kernels: the finished dS / P_dropped tiles leave as two TMA stores
+    // (the tiles already have the 128-byte-swizzle layout; rows >= T and columns >= Tp are clipped by the tensor map)
+    if (lane == 0) {
+      const int bh = b * a.H + h;
+      for (int jt = 0; jt < n_kv; ++jt) {
+        mbar_wait(ds_ready, jt & 1);
+        tma_store_3d(&tmWS, smem + kOffDS, jt * BKV, i0, bh);
+        tma_store_3d(&tmWP, smem + kOffPD, jt * BKV, i0, bh);
+        bulk_commit();
+        bulk_wait_read<0>();
+        mbar_arrive(st_done);
+      }
+      bulk_wait_all();
+    }
   } else if (warp >= 4) {
     const int q = warp & 3, half = (warp - 4) >> 2;
     const int il = q * 32 + lane, row = i0 + il;
@@ -630,26 +654,22 @@ relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
           }
         }
       }
-      // the previous tile's dQ MMAs must have finished reading the dS / dS~ tiles before they are overwritten
-      if (jt > 0) mbar_wait(dq_done, (jt - 1) & 1);
-      // dS → A operand tile (K-major, swizzled) and → HBM staging (dS, P_dropped)
-      uint32_t dsp[16], pdp[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        dsp[k] = pack_bf16(ds[2 * k], ds[2 * k + 1]);
-        pdp[k] = pack_bf16(pd[2 * k], pd[2 * k + 1]);
+      // the previous tile's dQ MMAs and TMA stores must have finished reading the dS / dS~ / P tiles before they are
+      // overwritten
+      if (jt > 0) {
+        mbar_wait(dq_done, (jt - 1) & 1);
+        mbar_wait(st_done, (jt - 1) & 1);
       }
+      // dS → A operand tile (K-major, swizzled); dS and P_dropped also go to HBM from these tiles (store warp)
+      uint32_t dsp[16];
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int k = 0; k < 16; ++k) dsp[k] = pack_bf16(ds[2 * k], ds[2 * k + 1]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
         st_sw128(s_ds, il, half * 4 + c, make_uint4(dsp[4 * c], dsp[4 * c + 1], dsp[4 * c + 2], dsp[4 * c + 3]));
-      if (row < T) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (j0 + c * 8 < Tp) {
-            *reinterpret_cast<uint4*>(wds + (size_t)row * Tp + j0 + c * 8) = make_uint4(dsp[4 * c], dsp[4 * c + 1], dsp[4 * c + 2], dsp[4 * c + 3]);
-            *reinterpret_cast<uint4*>(wp + (size_t)row * Tp + j0 + c * 8) = make_uint4(pdp[4 * c], pdp[4 * c + 1], pdp[4 * c + 2], pdp[4 * c + 3]);
-          }
-        }
+        st_sw128(smem + kOffPD, il, half * 4 + c,
+                 make_uint4(pack_bf16(pd[8 * c], pd[8 * c + 1]), pack_bf16(pd[8 * c + 2], pd[8 * c + 3]),
+                            pack_bf16(pd[8 * c + 4], pd[8 * c + 5]), pack_bf16(pd[8 * c + 6], pd[8 * c + 7])));
       }
       // un-skewed copy: dS~[il][x] with x = j_local + 127 - il (a fixed 64-column window per row; the rest stays zero).
       // x = half*32 + cbase + sh + k: the 16-byte chunk part of the shift is address arithmetic, the remaining
@@ -744,7 +764,7 @@ int launch_relpos_attn_bwd_q_tc(const AttnArgs& a, const bf16* ctx, const float*
                                 bf16* dqkv, float* dbu, float* dbv, bf16* ws_ds, bf16* ws_p, bf16* ws_qu, int Tp, cudaStream_t st) {
   using namespace atb;
   B2C_REQUIRE(a.d % 8 == 0 && a.d / a.H == DK && Tp % 8 == 0, "relpos_attn_bwd_q_tc: head dim must be 64");
-  CUtensorMap tk, tv, tp, tdo;
+  CUtensorMap tk, tv, tp, tdo, tws, twp;
   {
     uint64_t dims[3] = {(uint64_t)3 * a.d, (uint64_t)a.T, (uint64_t)a.B};
     uint64_t strides[2] = {(uint64_t)3 * a.d * 2, (uint64_t)a.T * 3 * a.d * 2};
@@ -762,6 +782,13 @@ int launch_relpos_attn_bwd_q_tc(const AttnArgs& a, const bf16* ctx, const float*
     uint32_t dbox[3] = {(uint32_t)DK, (uint32_t)BQ, 1};
     rc = make_tmap(&tdo, dctx, 2, 3, dd, dstr, dbox, es, 1);
     if (rc) return rc;
+    uint64_t wd[3] = {(uint64_t)Tp, (uint64_t)a.T, (uint64_t)a.B * a.H};
+    uint64_t wstr[2] = {(uint64_t)Tp * 2, (uint64_t)a.T * Tp * 2};
+    uint32_t wbox[3] = {(uint32_t)BKV, (uint32_t)BQ, 1};
+    rc = make_tmap(&tws, ws_ds, 2, 3, wd, wstr, wbox, es, 1);
+    if (rc) return rc;
+    rc = make_tmap(&twp, ws_p, 2, 3, wd, wstr, wbox, es, 1);
+    if (rc) return rc;
   }
   static bool set = false;
   if (!set) {
@@ -769,7 +796,7 @@ int launch_relpos_attn_bwd_q_tc(const AttnArgs& a, const bf16* ctx, const float*
     set = true;
   }
   relpos_attn_bwd_q_tc_kernel<<<dim3((a.T + BQ - 1) / BQ, a.H, a.B), kThreads, kSmem, st>>>(
-      tk, tv, tp, tdo, a, ctx32, ctx, dctx, lse, dqkv, dbu, dbv, ws_ds, ws_p, ws_qu, Tp);
+      tk, tv, tp, tdo, tws, twp, a, ctx32, ctx, dctx, lse, dqkv, dbu, dbv, ws_ds, ws_p, ws_qu, Tp);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
 }

@@ -66,16 +66,30 @@ struct SmemLayout {
 // a row (a thread-per-row store would touch 32 rows per instruction).  Ragged N falls back to per-thread stores.
 constexpr int EW = 16;
 
-// idx0 % 16 == 0 (the host requires N % 16 == 0 when dropout is on): one chunk hash, then a multiply-add per pair
+// idx0 % 16 == 0 (the host requires N % 16 == 0 when dropout is on): one chunk hash, then a multiply-add per pair; the
+// 16-bit lanes of the hash word are compared in place against the threshold shifted to the upper half
 __device__ __forceinline__ void dropout_ew(float (&v)[EW], const b2c_epilogue& e, uint64_t idx0) {
   static_assert(EW == 16, "one dropout chunk per epilogue chunk");
   const uint32_t base = dropout_base(e.seed, e.drop_site, idx0 >> 4);
+  const uint32_t keep_hi = e.drop_keep << 16;
 #pragma unroll
   for (int j = 0; j < EW; j += 2) {
     const uint32_t h = dropout_word(base, j >> 1);
-    v[j] = ((h & 0xFFFFu) < e.drop_keep) ? v[j] * e.drop_scale : 0.f;
-    v[j + 1] = ((h >> 16) < e.drop_keep) ? v[j + 1] * e.drop_scale : 0.f;
+    v[j] = ((h << 16) < keep_hi) ? v[j] * e.drop_scale : 0.f;
+    v[j + 1] = (h < keep_hi) ? v[j + 1] * e.drop_scale : 0.f;
   }
+}
+// round a pair to bf16 and back: one packed conversion + two bit operations (instead of four scalar conversions);
+// returns the packed word (low half = a)
+__device__ __forceinline__ uint32_t round_pair(float& a, float& b) {
+  const uint32_t w = pack_bf16(a, b);
+  a = __uint_as_float(w << 16);
+  b = __uint_as_float(w & 0xFFFF0000u);
+  return w;
+}
+__device__ __forceinline__ void round_ew(float (&v)[EW]) {
+#pragma unroll
+  for (int j = 0; j < EW; j += 2) round_pair(v[j], v[j + 1]);
 }
 __device__ __forceinline__ void load_bf16_ew(const bf16* p, float (&v)[EW]) {
 #pragma unroll
@@ -108,18 +122,22 @@ __device__ __forceinline__ void stage_store_bf16(uint8_t* stg, int lane, const f
 // same chunk through a TMA store: the 32 x 16 tile is written in the 32-byte-swizzle layout the tensor map expects
 // (16-byte unit k of row r at r*32 + ((k ^ ((r >> 2) & 1)) << 4)), one lane issues the bulk store of the box whose first
 // row is m_warp; rows >= M and columns >= N are clipped by the tensor map.  The caller has made sure `buf` is free.
-__device__ __forceinline__ void stage_tma_bf16(uint8_t* buf, int lane, const float (&v)[EW], const CUtensorMap* tm, int m_warp,
-                                               int n0) {
+__device__ __forceinline__ void stage_tma_words(uint8_t* buf, int lane, const uint32_t (&w)[EW / 2], const CUtensorMap* tm,
+                                                int m_warp, int n0) {
   const uint32_t sb = smem_u32(buf);
   const int f = (lane >> 2) & 1;
 #pragma unroll
-  for (int k = 0; k < 2; ++k)
-    sts128(sb + lane * 32 + ((k ^ f) << 4),
-           make_uint4(pack_bf16(v[8 * k], v[8 * k + 1]), pack_bf16(v[8 * k + 2], v[8 * k + 3]),
-                      pack_bf16(v[8 * k + 4], v[8 * k + 5]), pack_bf16(v[8 * k + 6], v[8 * k + 7])));
+  for (int k = 0; k < 2; ++k) sts128(sb + lane * 32 + ((k ^ f) << 4), make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]));
   fence_proxy_async();
   __syncwarp();
   if (lane == 0) tma_store_2d(tm, buf, n0, m_warp);
+}
+__device__ __forceinline__ void stage_tma_bf16(uint8_t* buf, int lane, const float (&v)[EW], const CUtensorMap* tm, int m_warp,
+                                               int n0) {
+  uint32_t w[EW / 2];
+#pragma unroll
+  for (int j = 0; j < EW / 2; ++j) w[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+  stage_tma_words(buf, lane, w, tm, m_warp, n0);
 }
 // fp32 chunk (32 rows x 16 cols = 64 B per row): out = residual + v, 8 rows x 64 B per store instruction.
 // The residual (aux) tile is fetched by resid_prefetch() BEFORE the epilogue maths so its latency is hidden.
@@ -322,23 +340,27 @@ __device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int
   if (MODE == B2C_EPI_BF16) {
     store_out0_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0, ts, to);
   } else if (MODE == B2C_EPI_SILU) {
-    // z = bf16(acc+bias) → out0 ; h = bf16(dropout(silu(z))) → out1   (conformer_modules.py:383-385)
+    // z = bf16(acc+bias) → out0 ; h = bf16(dropout(bf16(silu(z)))) → out1   (conformer_modules.py:383-385)
     float h[EW];
+    uint32_t zw[EW / 2];
 #pragma unroll
-    for (int j = 0; j < EW; ++j) {
-      v[j] = bf16_round(v[j]);
+    for (int j = 0; j < EW; j += 2) {
+      zw[j >> 1] = round_pair(v[j], v[j + 1]);
       h[j] = silu_f(v[j]);
+      h[j + 1] = silu_f(v[j + 1]);
     }
     if (e.drop_keep != 0) {
-#pragma unroll
-      for (int j = 0; j < EW; ++j) h[j] = bf16_round(h[j]);
+      round_ew(h);
       dropout_ew(h, e, didx);
     }
     if (ts) {
+      uint32_t hw[EW / 2];
+#pragma unroll
+      for (int j = 0; j < EW / 2; ++j) hw[j] = pack_bf16(h[2 * j], h[2 * j + 1]);
       if (lane == 0) bulk_wait_read<0>();
       __syncwarp();
-      stage_tma_bf16(stg, lane, v, to.tm0, to.m_warp, n0);
-      stage_tma_bf16(stg + 1024, lane, h, to.tm1, to.m_warp, n0);
+      stage_tma_words(stg, lane, zw, to.tm0, to.m_warp, n0);
+      stage_tma_words(stg + 1024, lane, hw, to.tm1, to.m_warp, n0);
       if (lane == 0) bulk_commit();
     } else {
       stage_store_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0);
@@ -346,8 +368,7 @@ __device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int
     }
   } else if (MODE == B2C_EPI_RESID_F32) {
     // out0_f32 = (aux_f32 ? aux : 0) + alpha * dropout(bf16(acc+bias))
-#pragma unroll
-    for (int j = 0; j < EW; ++j) v[j] = bf16_round(v[j]);
+    round_ew(v);
     if (e.drop_keep != 0) dropout_ew(v, e, didx);
 #pragma unroll
     for (int j = 0; j < EW; ++j) v[j] *= e.alpha;
@@ -357,8 +378,7 @@ __device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int
     float u[EW / 2];
 #pragma unroll
     for (int j = 0; j < EW; j += 2) {
-      v[j] = bf16_round(v[j]);
-      v[j + 1] = bf16_round(v[j + 1]);
+      round_pair(v[j], v[j + 1]);
       u[j >> 1] = valid ? v[j] * sigmoid_f(v[j + 1]) : 0.f;
     }
     store_out0_bf16(stg, lane, v, reinterpret_cast<bf16*>(e.out0), ldo, m, M, n0, ts, to);
@@ -369,8 +389,7 @@ __device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int
     // dz = bf16(dropout(bf16(acc)) * silu'(z)),  z = aux (bf16)
     float zz[EW];
     unpack_aux(auxc, zz);
-#pragma unroll
-    for (int j = 0; j < EW; ++j) v[j] = bf16_round(v[j]);
+    round_ew(v);
     if (e.drop_keep != 0) dropout_ew(v, e, didx);
 #pragma unroll
     for (int j = 0; j < EW; ++j) v[j] *= dsilu_f(zz[j]);

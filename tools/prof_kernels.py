@@ -56,12 +56,15 @@ lengths = torch.full((B,), T, dtype=torch.int32, device=DEV)
 gw = torch.zeros(FF, D, device=DEV)
 dz = rnd(M, FF)
 
-timed("ffn1 fwd  silu  24000x2048x512", lambda: L.gemm(x16, w1, M, FF, D, D, D, 0, 0, L.EPI_SILU, out0=hcopy, out1=z, bias=b1),
-      2.0 * M * FF * D)
+timed("ffn1 fwd  silu  24000x2048x512 p=.1", lambda: L.gemm(x16, w1, M, FF, D, D, D, 0, 0, L.EPI_SILU, out0=z, out1=hcopy, bias=b1,
+                                                              seed=1, drop_site=5, drop_p=0.1), 2.0 * M * FF * D)
 timed("ffn2 fwd  resid 24000x512x2048", lambda: L.gemm(hcopy, w2, M, D, FF, FF, FF, 0, 0, L.EPI_RESID_F32, out0=resid_out,
                                                         aux=resid, bias=b2, alpha=0.5), 2.0 * M * FF * D)
 timed("qkv  fwd  bf16  24000x1536x512", lambda: L.gemm(x16, wqkv, M, 3 * D, D, D, D, 0, 0, L.EPI_BF16, out0=out16), 2.0 * M * 3 * D * D)
-timed("ffn2 dgrad bf16 24000x2048x512", lambda: L.gemm(x16, w2, M, FF, D, D, FF, 0, 1, L.EPI_BF16, out0=z), 2.0 * M * FF * D)
+dzz = torch.empty(M, FF, dtype=torch.bfloat16, device=DEV)
+timed("ffn2 dgrad dsilu 24000x2048x512 p=.1", lambda: L.gemm(x16, w2, M, FF, D, D, FF, 0, 1, L.EPI_DSILU, out0=dzz, aux=z, seed=1,
+                                                               drop_site=5, drop_p=0.1), 2.0 * M * FF * D)
+timed("ffn2 dgrad bf16 24000x2048x512", lambda: L.gemm(x16, w2, M, FF, D, D, FF, 0, 1, L.EPI_BF16, out0=dzz), 2.0 * M * FF * D)
 timed("ffn1 dgrad bf16 24000x512x2048", lambda: L.gemm(dz, w1, M, D, FF, FF, D, 0, 1, L.EPI_BF16, out0=x16.clone()), 2.0 * M * FF * D)
 timed("ffn1 wgrad acc  2048x512x24000", lambda: L.gemm(dz, x16, FF, D, M, FF, D, 1, 1, L.EPI_ACCUM_F32, out0=gw), 2.0 * M * FF * D)
 gw2 = torch.zeros(D, FF, device=DEV)
