@@ -27,9 +27,8 @@ constexpr int kQBytes = BQ * DK * 2;                      // 16 KB each (q+u, q+
 constexpr int kProbBytes = BQ * BKV * 2;                  // 16 KB
 constexpr int kOffQu = 0, kOffQv = kQBytes, kOffProb = 2 * kQBytes, kOffStage = 2 * kQBytes + kProbBytes;
 constexpr int kOffBar = kOffStage + kStages * kStageBytes;
-constexpr int kOffMax = kOffBar + 256;  // float [3][2][128] row-max / row-sum exchange between the two halves of a row
-constexpr int kSmem = kOffMax + 3 * 2 * 128 * 4 + 1024;
-constexpr int kThreads = 128 + 8 * 32;
+constexpr int kOffMax = kOffBar + 256;  // float [3][NT<=4][128] row-max / row-sum exchange between the threads of a row
+constexpr int kSmem = kOffMax + 3 * 4 * 128 * 4 + 1024;
 constexpr uint32_t kTmemS = 0, kTmemR = 64, kTmemO = 256;  // column offsets
 }  // namespace atc
 
@@ -71,12 +70,60 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
       : "memory");
 }
 
+// N consecutive fp32 columns of this thread's TMEM lane, N in {16, 32, 48, 64}
+template <int N>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[N]) {
+  static_assert(N == 16 || N == 32 || N == 48 || N == 64, "unsupported width");
+  if constexpr (N == 16) {
+    tmem_ld16(taddr, r);
+  } else if constexpr (N == 32) {
+    tmem_ld32(taddr, r);
+  } else if constexpr (N == 64) {
+    tmem_ld64(taddr, r);
+  } else {
+    tmem_ld32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+    tmem_ld16(taddr + 32, *reinterpret_cast<uint32_t(*)[16]>(&r[32]));
+  }
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&r)[N]) {
+  static_assert(N == 16 || N == 32, "unsupported width");
+  if constexpr (N == 16) tmem_st16(taddr, r);
+  else tmem_st32(taddr, r);
+}
+// Per-lane skew of the positional band: x holds CW + 32 consecutive band columns starting at the warp-uniform offset;
+// afterwards x[k] = band[sh + k] for k < CW (5-stage barrel shift by sh in [0, 32))
+template <int CW>
+__device__ __forceinline__ void band_shift(uint32_t (&x)[CW + 32], int sh) {
+#pragma unroll
+  for (int k = 0; k < CW + 16; ++k) x[k] = (sh & 16) ? x[k + 16] : x[k];
+#pragma unroll
+  for (int k = 0; k < CW + 8; ++k) x[k] = (sh & 8) ? x[k + 8] : x[k];
+#pragma unroll
+  for (int k = 0; k < CW + 4; ++k) x[k] = (sh & 4) ? x[k + 4] : x[k];
+#pragma unroll
+  for (int k = 0; k < CW + 2; ++k) x[k] = (sh & 2) ? x[k + 2] : x[k];
+#pragma unroll
+  for (int k = 0; k < CW; ++k) x[k] = (sh & 1) ? x[k + 1] : x[k];
+}
+
 // write 8 bf16 (one 16-byte chunk `chunk` of row `row`) into a [rows x 64] K-major tile with the 128 B UMMA swizzle
 __device__ __forceinline__ void st_sw128(uint8_t* tile, int row, int chunk, uint4 v) {
   sts128(smem_u32(tile) + row * 128 + ((chunk ^ (row & 7)) << 4), v);
 }
 
-__global__ void __launch_bounds__(atc::kThreads, 1)
+// NT softmax threads per query row (NT * 4 softmax warps): with 4 per row every scheduler has 4 softmax warps to hide
+// the TMEM / shared-memory / MUFU latencies of the others behind, and each thread's skew shifts 16 instead of 32 columns
+template <int NT>
+__global__ void __launch_bounds__(128 + NT * 128, 1)
 relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                           const __grid_constant__ CUtensorMap tmP, const AttnArgs a, bf16* __restrict__ ctx,
                           float* __restrict__ ctx32, float* __restrict__ lse_out) {
@@ -108,9 +155,9 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(sr_full, 1);
-    mbar_init(p_ready, 8);
+    mbar_init(p_ready, 4 * NT);
     mbar_init(o_full, 1);
-    mbar_init(sr_free, 8);
+    mbar_init(sr_free, 4 * NT);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -207,8 +254,9 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       }
     }
   } else if (warp >= 4) {
+    constexpr int CW = BKV / NT;         // key columns (and output columns) of the row owned by this thread
     const int q = warp & 3;              // TMEM lane quarter (= warp id % 4)
-    const int half = (warp - 4) >> 2;    // which 32 key columns / 32 output columns of the row this thread owns
+    const int cq = (warp - 4) >> 2;      // which CW-column slice
     const int il = q * 32 + lane;        // row inside the tile = TMEM lane
     const int row = i0 + il;
     const bool rvalid = row < len;
@@ -217,7 +265,7 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
     const int sh = 31 - lane;
     const float sc2 = a.scale * kLog2e;
     const uint64_t rbase = attn_row_base(a, b, h, row);
-    float* xch = reinterpret_cast<float*>(smem + kOffMax);  // [2][128]
+    float* xch = reinterpret_cast<float*>(smem + kOffMax);  // [3][NT][128]
     // Online softmax in the exp2 domain on the raw scores v = S + R: p = 2^(v*sc2 - m).  O accumulates in TMEM across
     // the key tiles; the reference maximum m is only moved (and O / l rescaled) when the running maximum has grown by
     // more than 2^8 since it was set, so most tiles touch neither O nor the o_full barrier.  The dropout scale 1/(1-p)
@@ -227,53 +275,48 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
     const uint32_t keep_hi = a.drop_keep << 16;  // 16-bit lanes of the hash word compared in place
 
     for (int jt = 0; jt < n_kv; ++jt) {
-      const int j0 = jt * BKV + half * 32;
+      const int j0 = jt * BKV + cq * CW;
       mbar_wait(sr_full, jt & 1);
       tc_fence_after();
-      float v[32];
+      float v[CW];
       {
-        uint32_t sa[32], x[64];
-        tmem_ld32(tlane + kTmemS + half * 32, sa);
-        tmem_ld64(tlane + kTmemR + (uint32_t)(cbase + half * 32), x);
+        uint32_t sa[CW], x[CW + 32];
+        tmem_ld_cols<CW>(tlane + kTmemS + cq * CW, sa);
+        tmem_ld_cols<CW + 32>(tlane + kTmemR + (uint32_t)(cbase + cq * CW), x);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(sr_free);
-        // barrel shift left by sh = 31 - lane: afterwards x[k] = R[cbase + half*32 + sh + k]
+        band_shift<CW>(x, sh);
 #pragma unroll
-        for (int k = 0; k < 48; ++k) x[k] = (sh & 16) ? x[k + 16] : x[k];
-#pragma unroll
-        for (int k = 0; k < 40; ++k) x[k] = (sh & 8) ? x[k + 8] : x[k];
-#pragma unroll
-        for (int k = 0; k < 36; ++k) x[k] = (sh & 4) ? x[k + 4] : x[k];
-#pragma unroll
-        for (int k = 0; k < 34; ++k) x[k] = (sh & 2) ? x[k + 2] : x[k];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) x[k] = (sh & 1) ? x[k + 1] : x[k];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(sa[k]) + __uint_as_float(x[k]);
+        for (int k = 0; k < CW; ++k) v[k] = __uint_as_float(sa[k]) + __uint_as_float(x[k]);
       }
       if (jt * BKV + BKV > len) {  // ragged last tile (CTA-uniform): keys beyond the length get probability 0
 #pragma unroll
-        for (int k = 0; k < 32; ++k) v[k] = (j0 + k < len) ? v[k] : -1e30f;
+        for (int k = 0; k < CW; ++k) v[k] = (j0 + k < len) ? v[k] : -1e30f;
       }
       float mx = v[0];
 #pragma unroll
-      for (int k = 1; k < 32; ++k) mx = fmaxf(mx, v[k]);
+      for (int k = 1; k < CW; ++k) mx = fmaxf(mx, v[k]);
       mx *= sc2;
-      // Row maximum across the two column halves.  Only tile 0 synchronises the two warps of a quarter; afterwards the
-      // reference follows the row maximum of the PREVIOUS tile (both halves read the same two values, so they always
+      // Row maximum across the NT column slices.  Only tile 0 synchronises the warps of a quarter; afterwards the
+      // reference follows the row maximum of the PREVIOUS tile (all slices read the same NT values, so they always
       // agree on it): 2^(v - m_ref) may then exceed 2^8 by however much this tile tops the last one — harmless in fp32 /
       // bf16, and it takes every named barrier out of the steady-state loop.
-      float* slot = xch + (jt % 3) * 256;
-      slot[half * 128 + il] = mx;
+      float* slot = xch + (jt % 3) * (NT * 128);
+      slot[cq * 128 + il] = mx;
       if (jt == 0) {
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-        m_ref = fmaxf(mx, slot[(half ^ 1) * 128 + il]);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(NT * 32) : "memory");
+        m_ref = mx;
+#pragma unroll
+        for (int o = 1; o < NT; ++o) m_ref = fmaxf(m_ref, slot[((cq + o) % NT) * 128 + il]);
       } else {
         // PV_{j-1} has retired: every softmax warp finished tile j-1 (its maximum is visible) and the P tile is free
         mbar_wait(o_full, (jt - 1) & 1);
-        const float seen = fmaxf(mx_prev, xch[((jt - 1) % 3) * 256 + (half ^ 1) * 128 + il]);
+        const float* pslot = xch + ((jt - 1) % 3) * (NT * 128);
+        float seen = mx_prev;
+#pragma unroll
+        for (int o = 1; o < NT; ++o) seen = fmaxf(seen, pslot[((cq + o) % NT) * 128 + il]);
         if (__any_sync(0xffffffffu, seen > m_ref + 8.f)) {
           // move the reference maximum of the rows that need it: O (TMEM, complete up to tile j-1) and l are rescaled
           const float m_new = (seen > m_ref + 8.f) ? seen : m_ref;
@@ -281,12 +324,12 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
           m_ref = m_new;
           l_run *= corr;
           tc_fence_after();
-          uint32_t ot[32];
-          tmem_ld32(tlane + kTmemO + half * 32, ot);
+          uint32_t ot[CW];
+          tmem_ld_cols<CW>(tlane + kTmemO + cq * CW, ot);
           tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 32; ++k) ot[k] = __float_as_uint(__uint_as_float(ot[k]) * corr);
-          tmem_st32(tlane + kTmemO + half * 32, ot);
+          for (int k = 0; k < CW; ++k) ot[k] = __float_as_uint(__uint_as_float(ot[k]) * corr);
+          tmem_st_cols<CW>(tlane + kTmemO + cq * CW, ot);
           tmem_st_wait();
         }
       }
@@ -294,7 +337,7 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       float rs = 0.f;
       uint32_t kbase = 0;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < CW / 8; ++c) {
         float p[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -310,7 +353,7 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
             p[k + 1] = (hw < keep_hi) ? p[k + 1] : 0.f;
           }
         }
-        st_sw128(prob, il, half * 4 + c,
+        st_sw128(prob, il, cq * (CW / 8) + c,
                  make_uint4(pack_bf16(p[0], p[1]), pack_bf16(p[2], p[3]), pack_bf16(p[4], p[5]), pack_bf16(p[6], p[7])));
       }
       l_run += rs;
@@ -319,37 +362,39 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
     }
-    float o[32];
+    float o[CW];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) o[k] = 0.f;
+    for (int k = 0; k < CW; ++k) o[k] = 0.f;
     if (n_kv > 0) {
       mbar_wait(o_full, (n_kv - 1) & 1);
       tc_fence_after();
-      uint32_t ot[32];
-      tmem_ld32(tlane + kTmemO + half * 32, ot);
+      uint32_t ot[CW];
+      tmem_ld_cols<CW>(tlane + kTmemO + cq * CW, ot);
       tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 32; ++k) o[k] = __uint_as_float(ot[k]);
+      for (int k = 0; k < CW; ++k) o[k] = __uint_as_float(ot[k]);
     }
-    // total row sum = sum of the two halves (same reference maximum)
-    xch[half * 128 + il] = l_run;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-    const float l_tot = l_run + xch[(half ^ 1) * 128 + il];
+    // total row sum = sum of the slices (same reference maximum)
+    xch[cq * 128 + il] = l_run;
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(NT * 32) : "memory");
+    float l_tot = l_run;
+#pragma unroll
+    for (int o2 = 1; o2 < NT; ++o2) l_tot += xch[((cq + o2) % NT) * 128 + il];
     if (row < T) {
       const float inv = (rvalid && l_tot > 0.f) ? a.drop_scale / l_tot : 0.f;  // fully-masked query rows output exactly 0
-      bf16* op = ctx + ((size_t)b * T + row) * a.d + h * DK + half * 32;
+      bf16* op = ctx + ((size_t)b * T + row) * a.d + h * DK + cq * CW;
 #pragma unroll
-      for (int k = 0; k < 32; k += 8)
+      for (int k = 0; k < CW; k += 8)
         *reinterpret_cast<uint4*>(op + k) =
             make_uint4(pack_bf16(o[k] * inv, o[k + 1] * inv), pack_bf16(o[k + 2] * inv, o[k + 3] * inv),
                        pack_bf16(o[k + 4] * inv, o[k + 5] * inv), pack_bf16(o[k + 6] * inv, o[k + 7] * inv));
       if (ctx32) {
-        float* o32 = ctx32 + ((size_t)b * T + row) * a.d + h * DK + half * 32;
+        float* o32 = ctx32 + ((size_t)b * T + row) * a.d + h * DK + cq * CW;
 #pragma unroll
-        for (int k = 0; k < 32; k += 4)
+        for (int k = 0; k < CW; k += 4)
           *reinterpret_cast<float4*>(o32 + k) = make_float4(o[k] * inv, o[k + 1] * inv, o[k + 2] * inv, o[k + 3] * inv);
       }
-      if (lse_out && half == 0) lse_out[((size_t)b * a.H + h) * T + row] = (rvalid && l_tot > 0.f) ? m_ref + log2f(l_tot) : 0.f;
+      if (lse_out && cq == 0) lse_out[((size_t)b * a.H + h) * T + row] = (rvalid && l_tot > 0.f) ? m_ref + log2f(l_tot) : 0.f;
     }
   }
   tc_fence_before();
@@ -378,12 +423,16 @@ int launch_relpos_attn_fwd_tc(const AttnArgs& a, bf16* ctx, float* ctx32, float*
     rc = make_tmap(&tp, a.pos, 2, 2, pd, ps, pb, pe, 1);
     if (rc) return rc;
   }
-  static bool set = false;
-  if (!set) {
-    B2C_CUDA(cudaFuncSetAttribute(relpos_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    set = true;
+  static int nt = 0;  // softmax threads per row: 4 (default) or 2 (B2C_ATTN_NT=2)
+  if (nt == 0) {
+    const char* e = getenv("B2C_ATTN_NT");
+    nt = (e && atoi(e) == 2) ? 2 : 4;
+    B2C_CUDA(cudaFuncSetAttribute(relpos_attn_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    B2C_CUDA(cudaFuncSetAttribute(relpos_attn_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   }
-  relpos_attn_fwd_tc_kernel<<<dim3((a.T + BQ - 1) / BQ, a.H, a.B), kThreads, kSmem, st>>>(tk, tv, tp, a, ctx, ctx32, lse);
+  const dim3 grid((a.T + BQ - 1) / BQ, a.H, a.B);
+  if (nt == 2) relpos_attn_fwd_tc_kernel<2><<<grid, 128 + 2 * 128, kSmem, st>>>(tk, tv, tp, a, ctx, ctx32, lse);
+  else relpos_attn_fwd_tc_kernel<4><<<grid, 128 + 4 * 128, kSmem, st>>>(tk, tv, tp, a, ctx, ctx32, lse);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
 }
@@ -405,14 +454,14 @@ constexpr int kOffQu = 0, kOffQv = kTile, kOffDO = 2 * kTile, kOffDS = 3 * kTile
 constexpr int kOffPD = 7 * kTile;  // P_dropped tile, only staged for the TMA store to the key-side workspace
 constexpr int kOffStage = 8 * kTile;
 constexpr int kOffBar = kOffStage + kStages * kStageBytes;
-constexpr int kOffXch = kOffBar + 256;            // float [2][128]
-constexpr int kOffXch2 = kOffXch + 2 * 128 * 4;   // uint4 [2][128]: half 0 → half 1 boundary chunk of the un-skewed row
-constexpr int kSmem = kOffXch2 + 2 * 128 * 16 + 1024;
-constexpr int kThreads = 128 + 8 * 32;
+constexpr int kOffXch = kOffBar + 256;            // float [128] delta
+constexpr int kOffXch2 = kOffXch + 128 * 4;       // uint4 [2][NT-1 <= 3][128]: boundary chunks of the un-skewed row slices
+constexpr int kSmem = kOffXch2 + 2 * 3 * 128 * 16 + 1024;
 constexpr uint32_t kTmS = 0, kTmR = 64, kTmDP = 256, kTmDQU = 320, kTmDQV = 384;
 }  // namespace atb
 
-__global__ void __launch_bounds__(atb::kThreads, 1)
+template <int NT>
+__global__ void __launch_bounds__(128 + NT * 128, 1)
 relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                             const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmDO,
                             const __grid_constant__ CUtensorMap tmWS, const __grid_constant__ CUtensorMap tmWP, const AttnArgs a,
@@ -445,7 +494,7 @@ relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(srd_full, 1); mbar_init(srd_free, 8); mbar_init(ds_ready, 8); mbar_init(dq_done, 1); mbar_init(do_full, 1); mbar_init(st_done, 1);
+    mbar_init(srd_full, 1); mbar_init(srd_free, 4 * NT); mbar_init(ds_ready, 4 * NT); mbar_init(dq_done, 1); mbar_init(do_full, 1); mbar_init(st_done, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -588,7 +637,10 @@ relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
       bulk_wait_all();
     }
   } else if (warp >= 4) {
-    const int q = warp & 3, half = (warp - 4) >> 2;
+    constexpr int CW = BKV / NT;   // key columns of the row owned by this thread (and dq columns in the epilogue)
+    constexpr int PW = CW / 2;     // ... as packed bf16 pairs
+    constexpr int NC = PW / 4 + 1; // 16-byte chunks the un-skewed slice can touch
+    const int q = warp & 3, cq = (warp - 4) >> 2;
     const int il = q * 32 + lane, row = i0 + il;
     const bool rvalid = row < len;
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -607,35 +659,26 @@ relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
     uint8_t* s_dsu = smem + kOffDSU;
 
     for (int jt = 0; jt < n_kv; ++jt) {
-      const int j0 = jt * BKV + half * 32;
+      const int j0 = jt * BKV + cq * CW;
       mbar_wait(srd_full, jt & 1);
       tc_fence_after();
-      float ds[32], pd[32];
+      float ds[CW], pd[CW];
       {
-        uint32_t sa[32], x[64], dpv[32];
-        tmem_ld32(tlane + kTmS + half * 32, sa);
-        tmem_ld64(tlane + kTmR + (uint32_t)(cbase + half * 32), x);
-        tmem_ld32(tlane + kTmDP + half * 32, dpv);
+        uint32_t sa[CW], x[CW + 32], dpv[CW];
+        tmem_ld_cols<CW>(tlane + kTmS + cq * CW, sa);
+        tmem_ld_cols<CW + 32>(tlane + kTmR + (uint32_t)(cbase + cq * CW), x);
+        tmem_ld_cols<CW>(tlane + kTmDP + cq * CW, dpv);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(srd_free);
-#pragma unroll
-        for (int k = 0; k < 48; ++k) x[k] = (sh & 16) ? x[k + 16] : x[k];
-#pragma unroll
-        for (int k = 0; k < 40; ++k) x[k] = (sh & 8) ? x[k + 8] : x[k];
-#pragma unroll
-        for (int k = 0; k < 36; ++k) x[k] = (sh & 4) ? x[k + 4] : x[k];
-#pragma unroll
-        for (int k = 0; k < 34; ++k) x[k] = (sh & 2) ? x[k + 2] : x[k];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) x[k] = (sh & 1) ? x[k + 1] : x[k];
+        band_shift<CW>(x, sh);
         // p = 2^((S+R)*sc2 - lse) (lse = +huge for padded query rows → 0; padded keys of the ragged last tile → 0),
         // pd = dropout(p), ds = p * (dropout(dP) - delta) / sqrt(dk)
         const bool ragged = jt * BKV + BKV > len;  // CTA-uniform
         uint32_t kbase = 0;
 #pragma unroll
-        for (int k = 0; k < 32; k += 2) {
+        for (int k = 0; k < CW; k += 2) {
           float km0 = a.drop_scale, km1 = a.drop_scale;
           if (a.drop_keep != 0) {
             if ((k & 15) == 0) kbase = attn_keep_base(a, rbase, j0 + k);
@@ -661,46 +704,48 @@ relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
         mbar_wait(st_done, (jt - 1) & 1);
       }
       // dS → A operand tile (K-major, swizzled); dS and P_dropped also go to HBM from these tiles (store warp)
-      uint32_t dsp[16];
+      uint32_t dsp[PW];
 #pragma unroll
-      for (int k = 0; k < 16; ++k) dsp[k] = pack_bf16(ds[2 * k], ds[2 * k + 1]);
+      for (int k = 0; k < PW; ++k) dsp[k] = pack_bf16(ds[2 * k], ds[2 * k + 1]);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        st_sw128(s_ds, il, half * 4 + c, make_uint4(dsp[4 * c], dsp[4 * c + 1], dsp[4 * c + 2], dsp[4 * c + 3]));
-        st_sw128(smem + kOffPD, il, half * 4 + c,
+      for (int c = 0; c < CW / 8; ++c) {
+        st_sw128(s_ds, il, cq * (CW / 8) + c, make_uint4(dsp[4 * c], dsp[4 * c + 1], dsp[4 * c + 2], dsp[4 * c + 3]));
+        st_sw128(smem + kOffPD, il, cq * (CW / 8) + c,
                  make_uint4(pack_bf16(pd[8 * c], pd[8 * c + 1]), pack_bf16(pd[8 * c + 2], pd[8 * c + 3]),
                             pack_bf16(pd[8 * c + 4], pd[8 * c + 5]), pack_bf16(pd[8 * c + 6], pd[8 * c + 7])));
       }
       // un-skewed copy: dS~[il][x] with x = j_local + 127 - il (a fixed 64-column window per row; the rest stays zero).
-      // x = half*32 + cbase + sh + k: the 16-byte chunk part of the shift is address arithmetic, the remaining
-      // (sh & 7) elements are a half-word funnel shift plus a 2-stage word barrel shift of the packed row.  The two
-      // halves of a row meet inside one chunk: half 0 hands its last (partial) chunk to half 1, which merges it.
+      // x = cq*CW + cbase + sh + k: the 16-byte chunk part of the shift is address arithmetic, the remaining
+      // (sh & 7) elements are a half-word funnel shift plus a 2-stage word barrel shift of the packed slice.  Adjacent
+      // slices of a row meet inside one chunk: each thread hands its last (partial) chunk to the next one, which merges it.
       {
         const int es = sh & 7;
         const uint32_t odd16 = (uint32_t)(es & 1) * 16u, wsh = (uint32_t)es >> 1;
-        uint32_t e[21];
+        uint32_t e[4 * NC + 1];
         e[0] = __funnelshift_l(0u, dsp[0], odd16);
 #pragma unroll
-        for (int k = 1; k < 16; ++k) e[k] = __funnelshift_l(dsp[k - 1], dsp[k], odd16);
-        e[16] = __funnelshift_l(dsp[15], 0u, odd16);
-        e[17] = e[18] = e[19] = e[20] = 0u;
+        for (int k = 1; k < PW; ++k) e[k] = __funnelshift_l(dsp[k - 1], dsp[k], odd16);
+        e[PW] = __funnelshift_l(dsp[PW - 1], 0u, odd16);
 #pragma unroll
-        for (int k = 19; k >= 2; --k) e[k] = (wsh & 2u) ? e[k - 2] : e[k];
+        for (int k = PW + 1; k <= 4 * NC; ++k) e[k] = 0u;
+#pragma unroll
+        for (int k = 4 * NC - 1; k >= 2; --k) e[k] = (wsh & 2u) ? e[k - 2] : e[k];
         if (wsh & 2u) e[0] = e[1] = 0u;
 #pragma unroll
-        for (int k = 19; k >= 1; --k) e[k] = (wsh & 1u) ? e[k - 1] : e[k];
+        for (int k = 4 * NC - 1; k >= 1; --k) e[k] = (wsh & 1u) ? e[k - 1] : e[k];
         if (wsh & 1u) e[0] = 0u;
-        const int cid0 = half * 4 + (cbase >> 3) + (sh >> 3);
-        const uint32_t xq = smem_u32(smem + kOffXch2) + (uint32_t)(((jt & 1) * 128 + il) * 16);
-        if (half == 0) sts128(xq, make_uint4(e[16], e[17], e[18], e[19]));
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-        if (half == 1) {
-          const uint4 lo = lds128(xq);
+        const int cid0 = cq * (CW / 8) + (cbase >> 3) + (sh >> 3);
+        const uint32_t xbase = smem_u32(smem + kOffXch2) + (uint32_t)((jt & 1) * (NT - 1) * 128 * 16);
+        if (cq < NT - 1)
+          sts128(xbase + (uint32_t)((cq * 128 + il) * 16), make_uint4(e[4 * NC - 4], e[4 * NC - 3], e[4 * NC - 2], e[4 * NC - 1]));
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(NT * 32) : "memory");
+        if (cq > 0) {
+          const uint4 lo = lds128(xbase + (uint32_t)(((cq - 1) * 128 + il) * 16));
           e[0] |= lo.x; e[1] |= lo.y; e[2] |= lo.z; e[3] |= lo.w;
         }
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-          if (c < 4 || half == 1) {
+        for (int c = 0; c < NC; ++c) {
+          if (c < NC - 1 || cq == NT - 1) {
             const int cid = cid0 + c;
             st_sw128(s_dsu + (cid >> 3) * kTile, il, cid & 7, make_uint4(e[4 * c], e[4 * c + 1], e[4 * c + 2], e[4 * c + 3]));
           }
@@ -713,42 +758,42 @@ relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
     }
     // key tiles entirely beyond the valid length: dS = P = 0 in the staging buffers
     if (row < T) {
-      for (int j = n_kv * BKV + half * 32; j < n_kv_all * BKV; j += 64)
+      for (int j = n_kv * BKV + cq * CW; j < n_kv_all * BKV; j += BKV)
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < CW / 8; ++c)
           if (j + c * 8 < Tp) {
             *reinterpret_cast<uint4*>(wds + (size_t)row * Tp + j + c * 8) = make_uint4(0, 0, 0, 0);
             *reinterpret_cast<uint4*>(wp + (size_t)row * Tp + j + c * 8) = make_uint4(0, 0, 0, 0);
           }
     }
     // dq = dQ_u + dQ_v; d(pos_bias_u/v) = column sums over rows
-    float du[32], dv[32];
+    float du[CW], dv[CW];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) du[k] = dv[k] = 0.f;
+    for (int k = 0; k < CW; ++k) du[k] = dv[k] = 0.f;
     if (n_kv > 0) {
       mbar_wait(dq_done, (n_kv - 1) & 1);
       tc_fence_after();
-      uint32_t t0[32], t1[32];
-      tmem_ld32(tlane + kTmDQU + half * 32, t0);
-      tmem_ld32(tlane + kTmDQV + half * 32, t1);
+      uint32_t t0[CW], t1[CW];
+      tmem_ld_cols<CW>(tlane + kTmDQU + cq * CW, t0);
+      tmem_ld_cols<CW>(tlane + kTmDQV + cq * CW, t1);
       tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 32; ++k) { du[k] = __uint_as_float(t0[k]); dv[k] = __uint_as_float(t1[k]); }
+      for (int k = 0; k < CW; ++k) { du[k] = __uint_as_float(t0[k]); dv[k] = __uint_as_float(t1[k]); }
     }
     if (row < T) {
-      bf16* op = dqkv + ((size_t)b * T + row) * ld + h * DK + half * 32;
+      bf16* op = dqkv + ((size_t)b * T + row) * ld + h * DK + cq * CW;
 #pragma unroll
-      for (int k = 0; k < 32; k += 8)
+      for (int k = 0; k < CW; k += 8)
         *reinterpret_cast<uint4*>(op + k) =
             make_uint4(pack_bf16(du[k] + dv[k], du[k + 1] + dv[k + 1]), pack_bf16(du[k + 2] + dv[k + 2], du[k + 3] + dv[k + 3]),
                        pack_bf16(du[k + 4] + dv[k + 4], du[k + 5] + dv[k + 5]), pack_bf16(du[k + 6] + dv[k + 6], du[k + 7] + dv[k + 7]));
     }
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
+    for (int k = 0; k < CW; ++k) {
       const float su = warp_sum(du[k]), sv2 = warp_sum(dv[k]);  // rows >= len contribute exact zeros
       if (lane == 0) {
-        atomicAdd(dbias_u + h * DK + half * 32 + k, su);
-        atomicAdd(dbias_v + h * DK + half * 32 + k, sv2);
+        atomicAdd(dbias_u + h * DK + cq * CW + k, su);
+        atomicAdd(dbias_v + h * DK + cq * CW + k, sv2);
       }
     }
   }
@@ -790,13 +835,20 @@ int launch_relpos_attn_bwd_q_tc(const AttnArgs& a, const bf16* ctx, const float*
     rc = make_tmap(&twp, ws_p, 2, 3, wd, wstr, wbox, es, 1);
     if (rc) return rc;
   }
-  static bool set = false;
-  if (!set) {
-    B2C_CUDA(cudaFuncSetAttribute(relpos_attn_bwd_q_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    set = true;
+  static int nt = 0;  // softmax threads per row: 4 (default) or 2 (B2C_ATTN_NT=2)
+  if (nt == 0) {
+    const char* e = getenv("B2C_ATTN_NT");
+    nt = (e && atoi(e) == 2) ? 2 : 4;
+    B2C_CUDA(cudaFuncSetAttribute(relpos_attn_bwd_q_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    B2C_CUDA(cudaFuncSetAttribute(relpos_attn_bwd_q_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   }
-  relpos_attn_bwd_q_tc_kernel<<<dim3((a.T + BQ - 1) / BQ, a.H, a.B), kThreads, kSmem, st>>>(
-      tk, tv, tp, tdo, tws, twp, a, ctx32, ctx, dctx, lse, dqkv, dbu, dbv, ws_ds, ws_p, ws_qu, Tp);
+  const dim3 grid((a.T + BQ - 1) / BQ, a.H, a.B);
+  if (nt == 2)
+    relpos_attn_bwd_q_tc_kernel<2><<<grid, 128 + 2 * 128, kSmem, st>>>(tk, tv, tp, tdo, tws, twp, a, ctx32, ctx, dctx, lse, dqkv, dbu, dbv,
+                                                                       ws_ds, ws_p, ws_qu, Tp);
+  else
+    relpos_attn_bwd_q_tc_kernel<4><<<grid, 128 + 4 * 128, kSmem, st>>>(tk, tv, tp, tdo, tws, twp, a, ctx32, ctx, dctx, lse, dqkv, dbu, dbv,
+                                                                       ws_ds, ws_p, ws_qu, Tp);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
 }
