@@ -279,9 +279,15 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), L.lib.b2c_launch_count() - launches0
 
+    # NVML is initialised (and queried once) BEFORE the warm-up: on some pool hosts the first NVML calls of a process
+    # stall kernel submission for 100-300 ms a moment later — inside the first timed steps if they come after warm-up
+    clocks = ClockSampler(local) if rank == 0 else None
+    if clocks is not None:
+        clocks.sample(n=1)
+        clocks.rows.clear()
+        clocks.cost.clear()
     for _ in range(max(args.warmup, 3)):
         step(wav_dev, len_dev, False)
-    clocks = ClockSampler(local) if rank == 0 else None
     ms, launches = timed(args.steps, False, sampler=clocks)
     clk = clocks.result() if rank == 0 else None
     step_ms_value = list(per_step)

@@ -103,6 +103,8 @@ __device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t (&r)
 // afterwards x[k] = band[sh + k] for k < CW (5-stage barrel shift by sh in [0, 32))
 template <int CW>
 __device__ __forceinline__ void band_shift(uint32_t (&x)[CW + 32], int sh) {
+  // (measured: the multiply-add form x[k]*m0 + x[k+s]*m1 on the FMA pipe is slower than these selects — the kernels are
+  // bound by issue slots, not by the ALU pipe width)
 #pragma unroll
   for (int k = 0; k < CW + 16; ++k) x[k] = (sh & 16) ? x[k + 16] : x[k];
 #pragma unroll
@@ -120,8 +122,8 @@ __device__ __forceinline__ void st_sw128(uint8_t* tile, int row, int chunk, uint
   sts128(smem_u32(tile) + row * 128 + ((chunk ^ (row & 7)) << 4), v);
 }
 
-// NT softmax threads per query row (NT * 4 softmax warps): with 4 per row every scheduler has 4 softmax warps to hide
-// the TMEM / shared-memory / MUFU latencies of the others behind, and each thread's skew shifts 16 instead of 32 columns
+// NT softmax threads per query row (NT * 4 softmax warps).  2 and 4 measure the same on B200: the kernel is bound by the
+// instruction issue rate of the softmax / skew / dropout arithmetic, not by latency
 template <int NT>
 __global__ void __launch_bounds__(128 + NT * 128, 1)
 relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -272,7 +274,7 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
     // is applied once, with the final 1/l.
     float m_ref = -1e30f, l_run = 0.f, mx_prev = -1e30f;
     uint8_t* prob = smem + kOffProb;
-    const uint32_t keep_hi = a.drop_keep << 16;  // 16-bit lanes of the hash word compared in place
+    const uint32_t keep_hi = dropout_keep_hi(a.drop_keep);  // 16-bit lanes of the hash word compared in place
 
     for (int jt = 0; jt < n_kv; ++jt) {
       const int j0 = jt * BKV + cq * CW;
@@ -348,9 +350,10 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
           if ((c & 1) == 0) kbase = attn_keep_base(a, rbase, j0 + c * 8);
 #pragma unroll
           for (int k = 0; k < 8; k += 2) {
-            const uint32_t hw = dropout_word(kbase, (c & 1) * 4 + (k >> 1));
-            p[k] = ((hw << 16) < keep_hi) ? p[k] : 0.f;
-            p[k + 1] = (hw < keep_hi) ? p[k + 1] : 0.f;
+            uint32_t w0, w1;
+            dropout_pair(kbase, (c & 1) * 4 + (k >> 1), w0, w1);
+            p[k] = (w0 < keep_hi) ? p[k] : 0.f;
+            p[k + 1] = (w1 < keep_hi) ? p[k + 1] : 0.f;
           }
         }
         st_sw128(prob, il, cq * (CW / 8) + c,
@@ -423,10 +426,10 @@ int launch_relpos_attn_fwd_tc(const AttnArgs& a, bf16* ctx, float* ctx32, float*
     rc = make_tmap(&tp, a.pos, 2, 2, pd, ps, pb, pe, 1);
     if (rc) return rc;
   }
-  static int nt = 0;  // softmax threads per row: 4 (default) or 2 (B2C_ATTN_NT=2)
+  static int nt = 0;  // softmax threads per row: 2 (default) or 4 (B2C_ATTN_NT=4; measured equal: issue-slot bound)
   if (nt == 0) {
     const char* e = getenv("B2C_ATTN_NT");
-    nt = (e && atoi(e) == 2) ? 2 : 4;
+    nt = (e && atoi(e) == 4) ? 4 : 2;
     B2C_CUDA(cudaFuncSetAttribute(relpos_attn_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     B2C_CUDA(cudaFuncSetAttribute(relpos_attn_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   }
@@ -652,7 +655,7 @@ relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
     const float delta = xch[il];
     float lse2 = 1e30f;  // padded query rows: p = 0
     if (rvalid) lse2 = lse[((size_t)b * a.H + h) * T + row];
-    const uint32_t keep_hi = a.drop_keep << 16;  // 16-bit lanes of the hash word compared in place
+    const uint32_t keep_hi = dropout_keep_hi(a.drop_keep);  // 16-bit lanes of the hash word compared in place
     bf16* wds = ws_ds + ((size_t)(b * a.H + h) * T) * Tp;
     bf16* wp = ws_p + ((size_t)(b * a.H + h) * T) * Tp;
     uint8_t* s_ds = smem + kOffDS;
@@ -682,9 +685,10 @@ relpos_attn_bwd_q_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
           float km0 = a.drop_scale, km1 = a.drop_scale;
           if (a.drop_keep != 0) {
             if ((k & 15) == 0) kbase = attn_keep_base(a, rbase, j0 + k);
-            const uint32_t hw = dropout_word(kbase, (k & 15) >> 1);
-            km0 = ((hw << 16) < keep_hi) ? a.drop_scale : 0.f;
-            km1 = (hw < keep_hi) ? a.drop_scale : 0.f;
+            uint32_t w0, w1;
+            dropout_pair(kbase, (k & 15) >> 1, w0, w1);
+            km0 = (w0 < keep_hi) ? a.drop_scale : 0.f;
+            km1 = (w1 < keep_hi) ? a.drop_scale : 0.f;
           }
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
@@ -835,10 +839,10 @@ int launch_relpos_attn_bwd_q_tc(const AttnArgs& a, const bf16* ctx, const float*
     rc = make_tmap(&twp, ws_p, 2, 3, wd, wstr, wbox, es, 1);
     if (rc) return rc;
   }
-  static int nt = 0;  // softmax threads per row: 4 (default) or 2 (B2C_ATTN_NT=2)
+  static int nt = 0;  // softmax threads per row: 2 (default) or 4 (B2C_ATTN_NT=4; measured equal: issue-slot bound)
   if (nt == 0) {
     const char* e = getenv("B2C_ATTN_NT");
-    nt = (e && atoi(e) == 2) ? 2 : 4;
+    nt = (e && atoi(e) == 4) ? 4 : 2;
     B2C_CUDA(cudaFuncSetAttribute(relpos_attn_bwd_q_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     B2C_CUDA(cudaFuncSetAttribute(relpos_attn_bwd_q_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
   }

@@ -342,16 +342,26 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   return x;
 }
 // Dropout decisions come in 16-element chunks of the flat element index: one full hash per chunk (`dropout_base`) and
-// one multiply-add + xor-shift per element PAIR (`dropout_word`, two 16-bit lanes compared with the keep threshold).
+// two multiply-adds per element PAIR (`dropout_pair`: two words compared with the keep threshold in the upper half).
 // Hot loops that walk aligned chunks pay ~3 integer ops per pair; `dropout_hash(pair_idx)` is the same function for
 // arbitrary indices.
 __device__ __forceinline__ uint32_t dropout_base(uint64_t seed, uint32_t site, uint64_t chunk_idx) {
   return hash32((uint32_t)chunk_idx ^ (uint32_t)seed ^ ((uint32_t)(chunk_idx >> 32) * 0x9E3779B1U) ^ (site * 0x85EBCA77U) ^
                 __funnelshift_l((uint32_t)(seed >> 32), (uint32_t)(seed >> 32), 13));
 }
+// the two 32-bit words of element pair `pair` (0..7) of a chunk: element 2*pair is kept iff w0 < keep_hi, element
+// 2*pair+1 iff w1 < keep_hi, with keep_hi = dropout_keep_hi(keep16).  Two multiply-adds, no shifts or logic ops: the
+// integer multiplier shares the FMA pipe, the (scarcer) ALU pipe only sees the two compares.
+__device__ __forceinline__ void dropout_pair(uint32_t base, uint32_t pair, uint32_t& w0, uint32_t& w1) {
+  w0 = base * (0x9E3779B1U + 0x2545F492U * pair) + pair * 0x632BE5ABU;
+  w1 = w0 * 0x85EBCA77U + 0x165667B1U;
+}
+__device__ __forceinline__ uint32_t dropout_keep_hi(uint32_t keep16) { return (keep16 > 65535u ? 65535u : keep16) << 16; }
+// same decisions as one word with two 16-bit lanes ((h & 0xFFFF) < keep16, (h >> 16) < keep16) for the generic paths
 __device__ __forceinline__ uint32_t dropout_word(uint32_t base, uint32_t pair /* 0..7 */) {
-  const uint32_t w = base * (0x9E3779B1U + 0x2545F492U * pair) + pair * 0x632BE5ABU;
-  return w ^ (w >> 15);
+  uint32_t w0, w1;
+  dropout_pair(base, pair, w0, w1);
+  return (w0 >> 16) | (w1 & 0xFFFF0000U);
 }
 __device__ __forceinline__ uint32_t dropout_hash(uint64_t seed, uint32_t site, uint64_t pair_idx) {
   return dropout_word(dropout_base(seed, site, pair_idx >> 3), (uint32_t)pair_idx & 7u);

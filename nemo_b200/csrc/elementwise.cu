@@ -132,11 +132,14 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, 
           if (drop.keep != 0) {
             const uint64_t idx = (uint64_t)row * (uint64_t)d + (uint64_t)c * 4;
             const uint32_t hb = dropout_base(drop.seed, drop.site, idx >> 4);
-            const uint32_t h0 = dropout_word(hb, ((uint32_t)idx >> 1) & 7u), h1 = dropout_word(hb, (((uint32_t)idx >> 1) & 7u) + 1u);
-            n0 = ((h0 & 0xFFFFu) < drop.keep) ? n0 * drop.scale : 0.f;
-            n1 = ((h0 >> 16) < drop.keep) ? n1 * drop.scale : 0.f;
-            n2 = ((h1 & 0xFFFFu) < drop.keep) ? n2 * drop.scale : 0.f;
-            n3 = ((h1 >> 16) < drop.keep) ? n3 * drop.scale : 0.f;
+            const uint32_t khi = dropout_keep_hi(drop.keep);
+            uint32_t w0, w1, w2, w3;
+            dropout_pair(hb, ((uint32_t)idx >> 1) & 7u, w0, w1);
+            dropout_pair(hb, (((uint32_t)idx >> 1) & 7u) + 1u, w2, w3);
+            n0 = (w0 < khi) ? n0 * drop.scale : 0.f;
+            n1 = (w1 < khi) ? n1 * drop.scale : 0.f;
+            n2 = (w2 < khi) ? n2 * drop.scale : 0.f;
+            n3 = (w3 < khi) ? n3 * drop.scale : 0.f;
           }
           reinterpret_cast<uint2*>(next16 + (size_t)row * d)[c] = make_uint2(pack_bf16(n0, n1), pack_bf16(n2, n3));
         }

@@ -45,19 +45,23 @@ struct GemmParams {
   int splits;       // split-K factor (fp32 atomic accumulate epilogue only); conv wgrad: tap index
   int k_per_split;  // in units of BK blocks
   int tma_store;    // bf16 outputs leave through TMA stores (tensor maps tmC0 / tmC1) instead of per-thread stores
+  int tma_aux;      // the bf16 side input of the SiLU' epilogue arrives through TMA loads (tensor map tmAux)
   b2c_epilogue epi;
   ConvGeom cv;
 };
 
-template <int BN>
+template <int BN, bool AUX = false>
 struct SmemLayout {
-  static constexpr int kStages = (BN == 256) ? 6 : 8;
+  // AUX: the epilogue warps also stage a side input (2 x 1 KB per warp) — one pipeline stage fewer pays for it
+  static constexpr int kStages = (BN == 256) ? (AUX ? 5 : 6) : (AUX ? 6 : 8);
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = (BN / kCluster) * BK * 2;  // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarOffset = kStages * kStageBytes;
-  static constexpr int kStageOut = kBarOffset + 256;                 // per-epilogue-warp 2 KB output staging
-  static constexpr int kTotal = kStageOut + kEpiWarps * 2048 + 1024;  // + alignment slack
+  static constexpr int kAuxBar = kBarOffset + 256;                   // 2 mbarriers per epilogue warp (side-input loads)
+  static constexpr int kStageOut = kBarOffset + 512;                 // per-epilogue-warp 2 KB output staging
+  static constexpr int kStageAux = kStageOut + kEpiWarps * 2048;     // per-epilogue-warp 2 x 1 KB side-input staging
+  static constexpr int kTotal = kStageAux + (AUX ? kEpiWarps * 2048 : 0) + 1024;  // + alignment slack
 };
 
 // ---------------------------------------------------------------- epilogue
@@ -71,12 +75,13 @@ constexpr int EW = 16;
 __device__ __forceinline__ void dropout_ew(float (&v)[EW], const b2c_epilogue& e, uint64_t idx0) {
   static_assert(EW == 16, "one dropout chunk per epilogue chunk");
   const uint32_t base = dropout_base(e.seed, e.drop_site, idx0 >> 4);
-  const uint32_t keep_hi = e.drop_keep << 16;
+  const uint32_t keep_hi = dropout_keep_hi(e.drop_keep);
 #pragma unroll
   for (int j = 0; j < EW; j += 2) {
-    const uint32_t h = dropout_word(base, j >> 1);
-    v[j] = ((h << 16) < keep_hi) ? v[j] * e.drop_scale : 0.f;
-    v[j + 1] = (h < keep_hi) ? v[j + 1] * e.drop_scale : 0.f;
+    uint32_t w0, w1;
+    dropout_pair(base, j >> 1, w0, w1);
+    v[j] = (w0 < keep_hi) ? v[j] * e.drop_scale : 0.f;
+    v[j + 1] = (w1 < keep_hi) ? v[j + 1] * e.drop_scale : 0.f;
   }
 }
 // round a pair to bf16 and back: one packed conversion + two bit operations (instead of four scalar conversions);
@@ -413,8 +418,10 @@ __device__ __forceinline__ void epilogue_chunk(const b2c_epilogue& e, int m, int
 template <int BN, int A_MN, int B_MN, int MODE, int CONV = 0>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC0, const __grid_constant__ CUtensorMap tmC1, const GemmParams p) {
-  using L = SmemLayout<BN>;
+               const __grid_constant__ CUtensorMap tmC0, const __grid_constant__ CUtensorMap tmC1,
+               const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
+  constexpr bool kAux = (MODE == B2C_EPI_DSILU && CONV == 0);
+  using L = SmemLayout<BN, kAux>;
   constexpr int kStages = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -467,6 +474,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], kCluster * kEpiWarps);  // leader only: one arrive per epilogue warp of BOTH CTAs
     }
+    if (kAux)
+      for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(reinterpret_cast<uint64_t*>(smem + L::kAuxBar) + i, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2sm<2 * BN>(tmem_slot);
@@ -565,9 +574,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {
     const int q = warp & 3;             // TMEM lane quarter this warp may access (= warp id % 4)
     const int cgrp = (warp - 4) >> 2;   // four warps share a quarter and split the column chunks
+    constexpr int kChunks0 = BN / EW / (kEpiWarps / 4);
     uint8_t* stg = smem + L::kStageOut + (warp - 4) * 2048;
     TmaOut to;
     to.tm0 = &tmC0; to.tm1 = &tmC1; to.on = (CONV == 0) ? p.tma_store : 0; to.turn = 0; to.m_warp = 0;
+    // side input through TMA (SiLU' epilogue): 32-row x 16-column boxes into two 1 KB buffers, one mbarrier each
+    const bool aux_tma = kAux && p.tma_aux != 0;
+    uint8_t* aux_buf = smem + L::kStageAux + (warp - 4) * 2048;
+    uint64_t* aux_bar = reinterpret_cast<uint64_t*>(smem + L::kAuxBar) + (warp - 4) * 2;
+    uint32_t aux_use = 0;
+    if (aux_tma && lane == 0 && (int)blockIdx.x < total_tiles) {  // first chunk of the first tile
+      int mb0, nb0, sp0;
+      decode(blockIdx.x, mb0, nb0, sp0);
+      mbar_expect_tx(&aux_bar[0], 1024);
+      tma_load_2d(aux_buf, &tmAux, &aux_bar[0], nb0 * BN + cgrp * kChunks0 * EW, mb0 * BM + q * 32);
+    }
     int as = 0, aphase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       int m_blk, n_blk, split;
@@ -599,14 +620,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       to.m_warp = m0 + q * 32;
       // each warp owns kChunks CONSECUTIVE 16-column chunks (adjacent chunks of a row leave the SM back to back)
       tmem_ld16(trow + (uint32_t)(cgrp * kChunks * EW), acc[0]);
-      aux_prefetch<MODE>(auxc[0], epi, m, n0 + cgrp * kChunks * EW, m_bound, p.N);
+      if (!aux_tma) aux_prefetch<MODE>(auxc[0], epi, m, n0 + cgrp * kChunks * EW, m_bound, p.N);
 #pragma unroll
       for (int i = 0; i < kChunks; ++i) {
         const int c = cgrp * kChunks + i;
+        if (kAux && aux_tma) {
+          // side input of chunk i+1 (or of the next tile's first chunk) → the staging buffer chunk i-1 was read from
+          int nm = to.m_warp, nn = n0 + (c + 1) * EW;
+          bool more = true;
+          if (i + 1 == kChunks) {
+            const int nt = tile + gridDim.x;
+            more = nt < total_tiles;
+            if (more) {
+              int mb2, nb2, sp2;
+              decode(nt, mb2, nb2, sp2);
+              nm = mb2 * BM + q * 32;
+              nn = nb2 * BN + cgrp * kChunks * EW;
+            }
+          }
+          __syncwarp();
+          if (more && lane == 0) {
+            const int nb = (aux_use + 1) & 1;
+            mbar_expect_tx(&aux_bar[nb], 1024);
+            tma_load_2d(aux_buf + nb * 1024, &tmAux, &aux_bar[nb], nn, nm);
+          }
+          mbar_wait(&aux_bar[aux_use & 1], (aux_use >> 1) & 1);
+          const uint32_t ab = smem_u32(aux_buf + (aux_use & 1) * 1024) + lane * 32;
+          const int f = (lane >> 2) & 1;
+          auxc[i & 1].q[0] = lds128(ab + ((0 ^ f) << 4));
+          auxc[i & 1].q[1] = lds128(ab + ((1 ^ f) << 4));
+          ++aux_use;
+        }
         tmem_ld_wait();
         if (i + 1 < kChunks) {
           tmem_ld16(trow + (uint32_t)((c + 1) * EW), acc[(i + 1) & 1]);
-          aux_prefetch<MODE>(auxc[(i + 1) & 1], epi, m, n0 + (c + 1) * EW, m_bound, p.N);
+          if (!aux_tma) aux_prefetch<MODE>(auxc[(i + 1) & 1], epi, m, n0 + (c + 1) * EW, m_bound, p.N);
         }
         epilogue_chunk<MODE>(epi, m, n0 + c * EW, m_bound, p.N, acc[i & 1], auxc[i & 1], atomic, stg, lane, to);
         to.turn ^= 1;
@@ -660,11 +708,12 @@ static int g_gemm_impl = -1;  // 0 = tcgen05, 1 = simt (debug)
 
 template <int BN, int A_MN, int B_MN, int MODE, int CONV = 0>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream,
-                     const CUtensorMap* tc0 = nullptr, const CUtensorMap* tc1 = nullptr) {
+                     const CUtensorMap* tc0 = nullptr, const CUtensorMap* tc1 = nullptr, const CUtensorMap* taux = nullptr) {
   static const CUtensorMap kNoMap = {};
   const CUtensorMap& c0 = tc0 ? *tc0 : kNoMap;
   const CUtensorMap& c1 = tc1 ? *tc1 : (tc0 ? *tc0 : kNoMap);
-  using L = SmemLayout<BN>;
+  const CUtensorMap& cx = taux ? *taux : kNoMap;
+  using L = SmemLayout<BN, (MODE == B2C_EPI_DSILU && CONV == 0)>;
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, MODE, CONV>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -688,7 +737,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmPar
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   count_launch();
-  B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, c0, c1, p));
+  B2C_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, c0, c1, cx, p));
   return B2C_OK;
 }
 
@@ -769,7 +818,19 @@ static int dispatch_mode(const void* A, const void* B, int lda, int ldb, int a_m
     }
     p.tma_store = 1;
   }
-#define B2C_GO(BN_, AM_, BM_) return launch_tc<BN_, AM_, BM_, MODE>(ta, tb, p, stream, pc0, pc1)
+  // SiLU' epilogue: the bf16 side input (same shape / pitch as the output) arrives through TMA loads
+  CUtensorMap tax;
+  const CUtensorMap* pax = nullptr;
+  p.tma_aux = 0;
+  if (MODE == B2C_EPI_DSILU && p.tma_store && p.epi.aux && (reinterpret_cast<uintptr_t>(p.epi.aux) & 15) == 0) {
+    uint64_t dims[2] = {(uint64_t)p.N, (uint64_t)p.M}, strides[1] = {(uint64_t)p.epi.ldo * 2};
+    uint32_t box[2] = {(uint32_t)EW, 32}, es[2] = {1, 1};
+    int rc = make_tmap(&tax, p.epi.aux, 2, 2, dims, strides, box, es, 3);
+    if (rc) return rc;
+    pax = &tax;
+    p.tma_aux = 1;
+  }
+#define B2C_GO(BN_, AM_, BM_) return launch_tc<BN_, AM_, BM_, MODE>(ta, tb, p, stream, pc0, pc1, pax)
   if (BN == 256) {
     if (!a_mn && !b_mn) B2C_GO(256, 0, 0);
     if (!a_mn && b_mn) B2C_GO(256, 0, 1);
