@@ -229,6 +229,15 @@ def run_ours(args):
         return loss
 
     per_step = []
+    in_flight = []
+
+    def throttle(ev):
+        """The host may run at most two steps ahead of the GPU (the queue never drains, so nothing is lost): every step in
+        flight holds its own ~17 GB activation arena, and a host that gets a third step ahead makes the caching
+        allocator cudaMalloc another arena — a device-synchronising call that showed up as one 200-300 ms step."""
+        in_flight.append(ev)
+        if len(in_flight) > 2:
+            in_flight.pop(0).synchronize()
 
     def barrier():
         if world > 1:
@@ -261,6 +270,7 @@ def run_ours(args):
                 _ = loss.item()  # device→host read of the step's result
             marks.append(torch.cuda.Event(enable_timing=True))
             marks[-1].record()
+            throttle(marks[-1])
         e1.record()
         if sampler is not None:
             sampler.sample()  # GPU is still busy with the enqueued steps; nothing is left to submit
@@ -288,6 +298,9 @@ def run_ours(args):
         clocks.cost.clear()
     for _ in range(max(args.warmup, 3)):
         step(wav_dev, len_dev, False)
+        ev = torch.cuda.Event()
+        ev.record()
+        throttle(ev)
     ms, launches = timed(args.steps, False, sampler=clocks)
     clk = clocks.result() if rank == 0 else None
     step_ms_value = list(per_step)
