@@ -166,6 +166,10 @@ int b2c_subsample_conv1_fwd(const float* mel, const float* w, const float* bias,
 /* dw [C,9] += , dbias [C] +=  from dout [B,T1,F1,C] bf16 (already ReLU/mask-gated) */
 int b2c_subsample_conv1_bwd(const float* mel, const void* dout_bf16, const int32_t* len_in, float* dw, float* dbias,
                             int B, int F, int T, int C, void* stream);
+/* Tensor-core route for the same stem: im2col of the masked mel input into patches [B*T1*F1, 16] bf16 (columns 0..8 =
+ * the 3x3 window at kh*3+kw, column 9 = 1, 10..15 = 0).  Forward = b2c_gemm(patches, w16 [C,16], RELU_MASK epilogue);
+ * weight + bias gradient = b2c_gemm(dout^T, patches, ACCUM_F32) → [C,16] whose column 9 is the bias gradient. */
+int b2c_subsample_im2col(const float* mel, const int32_t* len_in, void* patches_bf16, int B, int F, int T, void* stream);
 /* Conv2d(C→C, 3x3, stride 2, pad 1) as an implicit GEMM on tcgen05 (9 shifted, strided 4-D TMA tile loads feed one
  * TMEM accumulator; no im2col): in [B,T1,F1,C] bf16 → out [B,T2,F2,C] bf16 = relu(conv+bias) * (t2 < len_out).
  * w_bf16 [C_out, 9*C_in] with k = (kh*3+kw)*C_in + ci. */

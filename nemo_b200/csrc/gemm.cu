@@ -492,8 +492,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int m_blk, n_blk, split;
         decode(tile, m_blk, n_blk, split);
         const int m0 = m_blk * BM, n0 = n_blk * BN + (int)crank * (BN / kCluster);  // this CTA's half of the B tile
-        const int kb0 = (CONV == 3) ? 0 : split * p.k_per_split;
-        const int kb1 = (CONV == 3) ? kb_total : min(kb_total, kb0 + p.k_per_split);
+        // conv weight-gradient: split = k_split * 9 + tap
+        const int kb0 = (CONV == 3) ? (split / 9) * p.k_per_split : split * p.k_per_split;
+        const int kb1 = min(kb_total, kb0 + p.k_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
@@ -519,7 +520,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // ---- B operand: this CTA's BN/2 rows (K-major) or columns (MN-major) of the tile
           if (CONV == 3) {
             const int bb = kb / p.cv.tiles_per_batch, t0 = (kb - bb * p.cv.tiles_per_batch) * p.cv.TR;
-            const int tap = split;  // kh*3 + kw
+            const int tap = split % 9;  // kh*3 + kw
 #pragma unroll
             for (int c = 0; c < BN / 64 / kCluster; ++c)
               tma_load_4d_2sm(sb + c * (64 * BK * 2), &tmB, fb, n0 + c * 64, tap % 3 - 1, 2 * t0 + tap / 3 - 1, bb);
@@ -545,8 +546,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int m_blk, n_blk, split;
         decode(tile, m_blk, n_blk, split);
-        const int kb0 = (CONV == 3) ? 0 : split * p.k_per_split;
-        const int kb1 = (CONV == 3) ? kb_total : min(kb_total, kb0 + p.k_per_split);
+        // conv weight-gradient: split = k_split * 9 + tap
+        const int kb0 = (CONV == 3) ? (split / 9) * p.k_per_split : split * p.k_per_split;
+        const int kb1 = min(kb_total, kb0 + p.k_per_split);
         mbar_wait(&tempty_bar[as], aphase ^ 1);  // both CTAs' epilogues have drained this accumulator stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
@@ -608,13 +610,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ? ((bb * p.cv.To + t * p.cv.ts + p.cv.pt) * p.cv.Fo + fl * p.cv.fs + p.cv.pf)
                 : m_bound;
       } else if (CONV == 3) {
-        epi.out0 = reinterpret_cast<float*>(epi.out0) + (size_t)split * p.cv.C;  // tap-major columns
+        epi.out0 = reinterpret_cast<float*>(epi.out0) + (size_t)(split % 9) * p.cv.C;  // tap-major columns
       }
       // software pipeline over this warp's column chunks: the TMEM load and the bf16 side input of chunk i+1 are in
       // flight while chunk i goes through the epilogue maths and the staged store
       constexpr int kChunks = BN / EW / (kEpiWarps / 4);
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-      const bool atomic = (CONV == 0 && p.splits > 1);
+      const bool atomic = (CONV == 0 && p.splits > 1) || (CONV == 3 && p.splits > 9);
       uint32_t acc[2][EW];
       AuxChunk auxc[2];
       to.m_warp = m0 + q * 32;
@@ -958,13 +960,24 @@ int conv3x3s2_bwd_weight(const void* dy, const void* x, float* dw, int B, int T1
   memset(&p, 0, sizeof(p));
   ConvGeom& g = p.cv;
   g.C = C; g.Fq = F2; g.TR = 64 / F2; g.Tq = T2; g.tiles_per_batch = (T2 + g.TR - 1) / g.TR;
-  p.M = C; p.N = C; p.K = B * g.tiles_per_batch; p.splits = 9; p.k_per_split = p.K;
+  p.M = C; p.N = C; p.K = B * g.tiles_per_batch;
+  // 256-wide tiles halve the operand traffic per flop (this GEMM is bound by L2 -> SM bandwidth); the contraction is
+  // split so that (pair-tiles x 9 taps x k-splits) still fills the CTA pairs
+  const bool wide = (C % 256 == 0);
+  const int bn = wide ? 256 : 128;
+  const int pair_tiles = ((C / BM + kCluster - 1) / kCluster) * (C / bn);
+  int ksplit = (num_sms() / kCluster) / (pair_tiles * 9);
+  if (ksplit < 1) ksplit = 1;
+  p.k_per_split = (p.K + ksplit - 1) / ksplit;
+  ksplit = (p.K + p.k_per_split - 1) / p.k_per_split;
+  p.splits = 9 * ksplit;
   p.epi.out0 = dw; p.epi.ldo = 9 * C; p.epi.alpha = 1.f;
   CUtensorMap ta, tb;
   int rc = conv_map4d(&ta, dy, C, F2, T2, B, 64, F2, g.TR, 1);
   if (rc) return rc;
   rc = conv_map4d(&tb, x, C, F1, T1, B, 64, F2, g.TR, 2);
   if (rc) return rc;
+  if (wide) return launch_tc<256, 1, 1, B2C_EPI_ACCUM_F32, 3>(ta, tb, p, stream);
   return launch_tc<128, 1, 1, B2C_EPI_ACCUM_F32, 3>(ta, tb, p, stream);
 }
 

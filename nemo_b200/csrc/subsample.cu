@@ -54,6 +54,43 @@ subsample_conv1_fwd_kernel(const float* __restrict__ mel, const float* __restric
   }
 }
 
+// im2col of the 1-channel stem for the tensor-core path: patches [B*T1*F1, 16] bf16, row (b,t1,f1) = the nine inputs
+// mask(mel)[b, 2f1-1+kw, 2t1-1+kh] at column kh*3+kw, 1.0 at column 9 (so the weight-gradient GEMM's column 9 is the
+// bias gradient), zeros in 10..15.  One CTA = 32 output time steps of one utterance; the mel tile is read once, coalesced.
+constexpr int kImT = 32;
+__global__ void __launch_bounds__(256)
+subsample_im2col_kernel(const float* __restrict__ mel, const int32_t* __restrict__ len_in, bf16* __restrict__ patches, int F,
+                        int T, int T1, int F1) {
+  extern __shared__ float tile[];  // [F][2*kImT + 3]
+  constexpr int W = 2 * kImT + 3;
+  const int b = blockIdx.y, t1_0 = blockIdx.x * kImT;
+  const int lin = len_in[b];
+  for (int i = threadIdx.x; i < F * W; i += blockDim.x) {
+    const int f = i / W, tt = i - f * W;
+    const int t = 2 * t1_0 - 1 + tt;
+    float v = 0.f;
+    if (tt < 2 * kImT + 1 && t >= 0 && t < T && t < lin) v = mel[((size_t)b * F + f) * T + t];
+    tile[i] = v;
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < kImT * F1; r += blockDim.x) {
+    const int tl = r / F1, f1 = r - tl * F1;
+    const int t1 = t1_0 + tl;
+    if (t1 >= T1) break;
+    float x[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int f = 2 * f1 - 1 + kw;
+        x[kh * 3 + kw] = (f >= 0 && f < F) ? tile[f * W + 2 * tl + kh] : 0.f;
+      }
+    uint4* dst = reinterpret_cast<uint4*>(patches + (((size_t)b * T1 + t1) * F1 + f1) * 16);
+    dst[0] = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+    dst[1] = make_uint4(pack_bf16(x[8], 1.f), 0u, 0u, 0u);
+  }
+}
+
 // dW[c, kh, kw] += sum dY[b,t1,f1,c] * x[b, 2t1+kh-1, 2f1+kw-1];  db[c] += sum dY   (dY already ReLU/mask gated)
 __global__ void __launch_bounds__(256)
 subsample_conv1_bwd_kernel(const float* __restrict__ mel, const bf16* __restrict__ dy, const int32_t* __restrict__ len_in,
@@ -245,6 +282,18 @@ extern "C" int b2c_subsample_conv1_fwd(const float* mel, const float* w, const f
   const int T1 = (T + 2 - 3) / 2 + 1, F1 = (F + 2 - 3) / 2 + 1;
   subsample_conv1_fwd_kernel<<<dim3(T1, B), 256, 3 * (F + 2) * sizeof(float), (cudaStream_t)stream>>>(
       mel, w, bias, len_in, len_out, reinterpret_cast<bf16*>(out_bf16), F, T, C, T1, F1);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_subsample_im2col(const float* mel, const int32_t* len_in, void* patches_bf16, int B, int F, int T,
+                                    void* stream) {
+  B2C_REQUIRE(B > 0 && T > 0 && F > 0, "subsample_im2col: bad shape");
+  const int T1 = (T + 2 - 3) / 2 + 1, F1 = (F + 2 - 3) / 2 + 1;
+  const size_t smem = (size_t)F * (2 * kImT + 3) * sizeof(float);
+  B2C_REQUIRE(smem <= 48 * 1024, "subsample_im2col: F = %d too large", F);
+  subsample_im2col_kernel<<<dim3((T1 + kImT - 1) / kImT, B), 256, smem, (cudaStream_t)stream>>>(
+      mel, len_in, reinterpret_cast<bf16*>(patches_bf16), F, T, T1, F1);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
 }

@@ -294,6 +294,14 @@ class B200ConformerEncoder(nn.Module):
         wc, pe = self._wc, self.pre_encode
         C, F2, d = pe._conv_channels, pe._f_out, self.d_model
         W = {}
+        w1 = pe.conv[0].weight  # [C,1,3,3] → [C,16] bf16: the 9 taps, then zeros (column 9 multiplies the patch's ones)
+
+        def build_w1():
+            w16 = torch.zeros(C, 16, dtype=F32, device=w1.device)
+            w16[:, :9] = w1.detach().reshape(C, 9)
+            return _cast(w16)
+
+        W["conv1"] = wc.get("conv1", [w1], build_w1)
         if self.subsampling == "striding":
             w2 = pe.conv[2].weight
             W["conv2"] = wc.get("conv2", [w2], lambda: _permute_bf16(w2, C, C, 9, 1).view(C, 9 * C))       # [co, tap, ci]
@@ -383,9 +391,15 @@ class _EncoderFn(torch.autograd.Function):
         enc_len32 = lens[-1]
 
         # ---- subsampling -------------------------------------------------------------------------------------
+        # stem Conv2d(1→C): im2col (K = 9 padded to 16, column 9 = 1) + tensor-core GEMM with the ReLU / time-mask
+        # epilogue — the direct stencil kernel is bound by CUDA-core FMA issue, this one by the output write
         x1 = _empty(B, Ts[1], Fs[1], C, dev=dev)
-        L.call("subsample_conv1_fwd", mel, pe.conv[0].weight.detach(), pe.conv[0].bias.detach(), len_in32, lens[0], x1,
-               B, Fm, Tm, C)
+        rows1 = B * Ts[1] * Fs[1]
+        patches = _empty(rows1, 16, dev=dev)
+        L.call("subsample_im2col", mel, len_in32, patches, B, Fm, Tm)
+        _gemm(patches, W["conv1"], rows1, C, 16, L.EPI_RELU_MASK, out0=x1, bias=pe.conv[0].bias.detach(), lengths=lens[0],
+              rows_per_batch=Ts[1] * Fs[1], rows_inner=Fs[1])
+        S["patches"] = patches
         if enc.subsampling == "striding":
             x2 = _empty(B, Ts[2], Fs[2], C, dev=dev)
             L.call("conv3x3s2_fwd", x1, W["conv2"], pe.conv[2].bias.detach(), lens[1], x2, B, Ts[1], Fs[1], C)
@@ -632,6 +646,15 @@ class _EncoderFn(torch.autograd.Function):
         dylast = _empty(M, F2 * C, dev=dev)
         _gemm(t16, W["out"], M, F2 * C, d, L.EPI_RELU_BWD, b_mn=1, ldb=F2 * C, out0=dylast, aux=xlast.view(M, F2 * C))
         Ts, Fs, lens = mt["Ts"], mt["Fs"], mt["lens"]
+
+        def conv1_bwd(dy1):
+            # [C,16] += dY^T · patches: columns 0..8 are the stem's weight gradient, column 9 (ones) its bias gradient
+            rows1 = B * Ts[1] * Fs[1]
+            g16 = arena.zeros(C, 16)
+            _gemm(dy1, ctx.S["patches"], C, 16, rows1, L.EPI_ACCUM_F32, a_mn=1, b_mn=1, lda=C, ldb=16, out0=g16, ldo=16)
+            G["pre_encode.conv.0.weight"].view(C, 9).add_(g16[:, :9])
+            G["pre_encode.conv.0.bias"].add_(g16[:, 9])
+
         if enc.subsampling == "striding":
             x1, x2 = ctx.S["sub"]
             gw2 = arena.zeros(C, 9 * C)
@@ -640,8 +663,7 @@ class _EncoderFn(torch.autograd.Function):
             L.call("colsum_bf16", dylast, G["pre_encode.conv.2.bias"], B * Ts[2] * Fs[2], C, C)
             dx1 = _empty(B, Ts[1], Fs[1], C, dev=dev)
             L.call("conv3x3s2_bwd_data", dylast, W["conv2_d"], x1, dx1, B, Ts[1], Fs[1], C)
-            L.call("subsample_conv1_bwd", mt["mel"], dx1, mt["len_in32"], G["pre_encode.conv.0.weight"],
-                   G["pre_encode.conv.0.bias"], B, Fs[0], Ts[0], C)
+            conv1_bwd(dx1)
         else:
             # dw_striding: x1 → [dw(ci) → pw(ci+1) + ReLU] x 2;  acts = [x1, dw2, pw3, dw5, pw6]
             acts = ctx.S["sub"]
@@ -658,8 +680,7 @@ class _EncoderFn(torch.autograd.Function):
                 L.call("dwconv3x3s2_bwd", ddw, xin, pe.conv[ci].weight.detach(), lens[s_i + 1], dxin,
                        G[f"pre_encode.conv.{ci}.weight"], G[f"pre_encode.conv.{ci}.bias"], B, Ts[s_i + 1], Fs[s_i + 1], C)
                 dyc = dxin
-            L.call("subsample_conv1_bwd", mt["mel"], dyc, mt["len_in32"], G["pre_encode.conv.0.weight"],
-                   G["pre_encode.conv.0.bias"], B, Fs[0], Ts[0], C)
+            conv1_bwd(dyc)
         if fg is not None:
             fg.ready(*fg.span("pre_encode."))
             return (None,) * (3 + len(plist))
