@@ -74,7 +74,48 @@ def ncu_raw(rep, name, pattern):
             w.writerow(out)
 
 
+def ncu_kernels():
+    """gpurun_out/prof_kernels_raw.csv (text export of `ncu --set full` over tools/prof_kernels.py, written on the GPU box
+    by tools/gpu_prof3.sh — the .ncu-rep itself exceeds the return limit) → profiles/<tag>_ncu_kernels.md"""
+    p = os.path.join(G, "prof_kernels_raw.csv")
+    if not os.path.exists(p):
+        return
+    rows = list(csv.reader(open(p)))
+    hdr = rows[0]
+    col = {h: i for i, h in enumerate(hdr)}
+    stall = [h for h in hdr if "smsp__average_warps_issue_stalled" in h and h.endswith("_per_issue_active.ratio")]
+    sel = [("gpu__time_duration.sum", "time us"), ("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"),
+           ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"), ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
+           ("l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed", "LSU %"),
+           ("dram__bytes_read.sum", "DRAM rd MB"), ("dram__bytes_write.sum", "DRAM wr MB"), ("launch__registers_per_thread", "regs")]
+    with open(os.path.join(out_dir, f"{tag}_ncu_kernels.md"), "w") as f:
+        f.write(f"# {tag}: `ncu --set full --clock-control none` over `tools/prof_kernels.py` (hot kernels alone at the bench shapes: "
+                "M = 24000 tokens, T = 750, 8 heads x 64, dropout 0.1)\n\n")
+        f.write("Times under ncu are serialised and cache-cold; `tools/prof_kernels.py --time` (CUDA events) gives the timings quoted "
+                "in DESIGN.md.  DRAM MB = `dram__bytes_read/write.sum` per launch.\n\n")
+        f.write("| kernel | " + " | ".join(n for _, n in sel) + " | top stalls (warp-cycles per issued instruction) |\n")
+        f.write("|---|" + "---:|" * len(sel) + "---|\n")
+        for r in rows[2:]:
+            name = re.sub(r"void |b2c::|\(.*", "", r[col["Kernel Name"]])[:60]
+            vals = []
+            for k, _ in sel:
+                v = r[col[k]] if k in col else ""
+                try:
+                    vals.append(f"{float(v):.1f}")
+                except ValueError:
+                    vals.append(v)
+            st = sorted(((float(r[col[h]] or 0), h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""))
+                         for h in stall), reverse=True)[:4]
+            f.write(f"| `{name}` | " + " | ".join(vals) + " | " + ", ".join(f"{b} {a:.2f}" for a, b in st) + " |\n")
+    kt = os.path.join(G, "kernel_times.log")
+    if os.path.exists(kt):
+        with open(os.path.join(out_dir, f"{tag}_kernel_times.txt"), "w") as f:
+            f.write("# tools/prof_kernels.py --time on one B200 (CUDA events, 20 iterations, 256 MB L2 flush between iterations)\n")
+            f.write(open(kt).read())
+
+
 launches()
+ncu_kernels()
 ncu_raw("prof_gemm.ncu-rep", "ncu_gemm", "gemm")
 ncu_raw("prof_attn.ncu-rep", "ncu_attn", "attn")
 ncu_raw("prof_ln.ncu-rep", "ncu_ln_dwconv", "ln")
