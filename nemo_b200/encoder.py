@@ -133,6 +133,25 @@ class _Arena:
         t.zero_()
         return t
 
+    def zeros_many(self, *shapes):
+        """fp32 accumulators of one layer out of ONE zeroed slab (one fill kernel instead of one per buffer)"""
+        sizes = []
+        for shp in shapes:
+            n = 1
+            for s_ in shp:
+                n *= int(s_)
+            sizes.append((n + 63) & ~63)
+        slab = self.alloc(sum(sizes), dtype=F32)
+        slab.zero_()
+        out, off = [], 0
+        for shp, n in zip(shapes, sizes):
+            m = 1
+            for s_ in shp:
+                m *= int(s_)
+            out.append(slab[off:off + m].view(*shp))
+            off += n
+        return out
+
 
 class _WeightCache:
     """bf16 operand copies of the fp32 master weights in the kernels' layouts, refreshed when a parameter changes
@@ -579,7 +598,7 @@ class _EncoderFn(torch.autograd.Function):
             L.call("colsum_bf16", t16, G[pfx + "conv.pointwise_conv2.bias"], M, d, d)
             ds = _empty(M, d, dev=dev)
             _gemm(t16, W[f"{li}.pw2"], M, d, d, L.EPI_BF16, b_mn=1, ldb=d, out0=ds)
-            sums = arena.zeros(2, d)
+            sums, gw, gb, dpos, gqkv, gqb = arena.zeros_many((2, d), (2 * d, d), (2 * d,), (2 * T - 1, d), (3 * d, d), (3 * d,))
             L.call("bn_silu_bwd_reduce", ds, c, bnp[0], bnp[1], bnp[2], bnp[3], sums[0], sums[1], M, d)
             dc = _empty(M, d, dev=dev)
             L.call("bn_silu_bwd_apply", ds, c, cv.batch_norm.weight.detach(), bnp[0], bnp[1], bnp[2], bnp[3], sums[0],
@@ -590,10 +609,8 @@ class _EncoderFn(torch.autograd.Function):
                    G[pfx + "conv.depthwise_conv.weight"], G[pfx + "conv.depthwise_conv.bias"], B, T, d, k)
             dg = _empty(M, 2 * d, dev=dev)
             L.call("glu_bwd", du, g, dg, M, d)
-            gw = arena.zeros(2 * d, d)  # interleaved layout
             wgrad(dg, 2 * d, y3, d, gw)
             _permute_f32(gw, d, 2, d, 0, out=G[pfx + "conv.pointwise_conv1.weight"], accumulate=1)
-            gb = arena.zeros(2 * d)
             L.call("colsum_bf16", dg, gb, M, 2 * d, 2 * d)
             _permute_f32(gb, d, 2, 1, 0, out=G[pfx + "conv.pointwise_conv1.bias"], accumulate=1)
             dy3 = _empty(M, d, dev=dev)
@@ -607,7 +624,6 @@ class _EncoderFn(torch.autograd.Function):
             dctx = _empty(M, d, dev=dev)
             _gemm(t16, W[f"{li}.o"], M, d, d, L.EPI_BF16, b_mn=1, ldb=d, out0=dctx)
             dqkv = _empty(M, 3 * d, dev=dev)
-            dpos = arena.zeros(2 * T - 1, d)
             nbytes = L.lib.b2c_relpos_attn_bwd_workspace(B, T, H)
             ws = enc.__dict__.get("_attn_ws")
             if ws is None or ws.numel() < nbytes or ws.device != dev:
@@ -616,9 +632,7 @@ class _EncoderFn(torch.autograd.Function):
             L.call("relpos_attn_bwd", qkv, pp, at.pos_bias_u.detach(), at.pos_bias_v.detach(), mt["lens"][-1], ctxv, ctx32, dctx, lse,
                    dqkv, dpos, G[pfx + "self_attn.pos_bias_u"], G[pfx + "self_attn.pos_bias_v"], ws, nbytes, B, T, H, dk,
                    p_att, seed, site + S_ATT_P)
-            gqkv = arena.zeros(3 * d, d)
             wgrad(dqkv, 3 * d, y2, d, gqkv)
-            gqb = arena.zeros(3 * d)
             L.call("colsum_bf16", dqkv, gqb, M, 3 * d, 3 * d)
             for j, nm in enumerate(("linear_q", "linear_k", "linear_v")):
                 G[f"{pfx}self_attn.{nm}.weight"].add_(gqkv[j * d:(j + 1) * d])
