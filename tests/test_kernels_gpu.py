@@ -434,3 +434,39 @@ def test_subsampling_convs(B, F, T, C):
     L.call("subsample_conv1_bwd", mel, dx1, l32, dw1, db1, B, F, T, C)
     report("conv1_bwd_dw", dw1.view(C, 1, 3, 3), w1r.grad, 1e-2)
     report("conv1_bwd_db", db1, b1r.grad, 1e-2)
+
+
+@pytest.mark.parametrize("B,F,T,C", [(2, 80, 131, 128), (3, 80, 301, 512)])
+def test_stem_as_im2col_gemm_matches_the_stencil_kernels(B, F, T, C):
+    """Conv2d(1→C) stem through the tensor-core route (im2col + K=16 GEMM) against the direct stencil kernels of the same
+    library (which test_subsampling_convs pins to torch): forward bit-compatible up to bf16 rounding, weight / bias
+    gradient from the GEMM's [C,16] output (column 9 = bias gradient)."""
+    lengths = torch.tensor([T, max(T - 37, 3), 9][:B], dtype=torch.int64, device=DEV)
+    l32 = torch.empty(B, dtype=torch.int32, device=DEV)
+    st = torch.empty(2 * B, dtype=torch.int32, device=DEV)
+    o64 = torch.empty(B, dtype=torch.int64, device=DEV)
+    L.call("subsample_lengths", lengths, l32, st, o64, B, 2)
+    len1 = st[:B]
+    T1, F1 = (T - 1) // 2 + 1, (F - 1) // 2 + 1
+    mel = rnd(B, F, T)  # NOT pre-masked: both routes apply the input length mask themselves
+    w1, b1 = rnd(C, 1, 3, 3, scale=0.3), rnd(C, scale=0.1)
+    x_ref = torch.empty(B, T1, F1, C, dtype=torch.bfloat16, device=DEV)
+    L.call("subsample_conv1_fwd", mel, w1, b1, l32, len1, x_ref, B, F, T, C)
+    rows = B * T1 * F1
+    patches = torch.empty(rows, 16, dtype=torch.bfloat16, device=DEV)
+    L.call("subsample_im2col", mel, l32, patches, B, F, T)
+    assert (patches[:, 9].float() == 1).all() and (patches[:, 10:].float() == 0).all()
+    w16 = torch.zeros(C, 16, device=DEV)
+    w16[:, :9] = w1.reshape(C, 9)
+    w16 = w16.to(torch.bfloat16)
+    x = torch.empty(B, T1, F1, C, dtype=torch.bfloat16, device=DEV)
+    L.gemm(patches, w16, rows, C, 16, 16, 16, 0, 0, L.EPI_RELU_MASK, out0=x, bias=b1, lengths=len1, rows_per_batch=T1 * F1,
+           rows_inner=F1)
+    report("stem_gemm_fwd", x, x_ref.float(), 1e-2)
+    dy = (rnd(B, T1, F1, C, seed=11) * (x_ref.float() > 0)).to(torch.bfloat16)
+    dw_ref, db_ref = torch.zeros(C, 9, device=DEV), torch.zeros(C, device=DEV)
+    L.call("subsample_conv1_bwd", mel, dy, l32, dw_ref, db_ref, B, F, T, C)
+    g16 = torch.zeros(C, 16, device=DEV)
+    L.gemm(dy, patches, C, 16, rows, C, 16, 1, 1, L.EPI_ACCUM_F32, out0=g16, ldo=16)
+    report("stem_gemm_dw", g16[:, :9], dw_ref, 1e-2)
+    report("stem_gemm_db", g16[:, 9], db_ref, 1e-2)
