@@ -141,14 +141,23 @@ bn_silu_bwd_reduce_kernel(const bf16* __restrict__ ds, const bf16* __restrict__ 
   const long long row0 = (long long)blockIdx.y * rows_per_cta;
   const long long row1 = min(M, row0 + rows_per_cta);
   float a0 = 0.f, a1 = 0.f, x0 = 0.f, x1 = 0.f;
-  for (long long r = row0; r < row1; ++r) {
-    const float2 cv = unpack_bf16(*reinterpret_cast<const uint32_t*>(c + r * d + ch));
-    const float2 dv = unpack_bf16(*reinterpret_cast<const uint32_t*>(ds + r * d + ch));
-    const float n0 = bf16_round(fmaf(cv.x, sc0, sh0)), n1 = bf16_round(fmaf(cv.y, sc1, sh1));
-    const float dz0 = dv.x * dsilu_f(n0), dz1 = dv.y * dsilu_f(n1);
-    a0 += dz0; a1 += dz1;
-    x0 += dz0 * (cv.x - m0) * r0;
-    x1 += dz1 * (cv.y - m1) * r1;
+  for (long long r = row0; r < row1; r += 4) {  // 8 independent loads in flight per thread
+    uint32_t cw[4], dw_[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool ok = r + k < row1;
+      cw[k] = ok ? __ldg(reinterpret_cast<const uint32_t*>(c + (r + k) * d + ch)) : 0u;
+      dw_[k] = ok ? __ldg(reinterpret_cast<const uint32_t*>(ds + (r + k) * d + ch)) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 cv = unpack_bf16(cw[k]), dv = unpack_bf16(dw_[k]);  // padded rows: ds = 0 → contribute nothing
+      const float n0 = bf16_round(fmaf(cv.x, sc0, sh0)), n1 = bf16_round(fmaf(cv.y, sc1, sh1));
+      const float dz0 = dv.x * dsilu_f(n0), dz1 = dv.y * dsilu_f(n1);
+      a0 += dz0; a1 += dz1;
+      x0 += dz0 * (cv.x - m0) * r0;
+      x1 += dz1 * (cv.y - m1) * r1;
+    }
   }
   atomicAdd(sum_dz + ch, a0); atomicAdd(sum_dz + ch + 1, a1);
   atomicAdd(sum_dz_xhat + ch, x0); atomicAdd(sum_dz_xhat + ch + 1, x1);
@@ -296,14 +305,111 @@ glu_bwd_kernel(const bf16* __restrict__ du, const bf16* __restrict__ g, bf16* __
   reinterpret_cast<uint32_t*>(dg)[i] = pack_bf16(dv * s, dv * ag.x * s * (1.f - s));
 }
 
+// ---- 8-wide variants (d % 8 == 0): one 16-byte load / store per tensor and thread — the 4-byte-per-thread versions above
+// keep too few bytes in flight to get near the HBM roofline
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+__global__ void __launch_bounds__(256)
+bn_silu_fwd8_kernel(const bf16* __restrict__ c, const float* __restrict__ scale, const float* __restrict__ shift,
+                    bf16* __restrict__ s, long long total8, int d) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  const int ch = (int)((i * 8) % d);
+  float x[8], sc[8], sh[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(c) + i), x);
+  ld8(scale + ch, sc);
+  ld8(shift + ch, sh);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = silu_f(bf16_round(fmaf(x[k], sc[k], sh[k])));
+  reinterpret_cast<uint4*>(s)[i] = pack8(x);
+}
+
+__global__ void __launch_bounds__(256)
+bn_silu_bwd_apply8_kernel(const bf16* __restrict__ ds, const bf16* __restrict__ c, const float* __restrict__ gamma,
+                          const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                          const float* __restrict__ rstd, const float* __restrict__ sum_dz,
+                          const float* __restrict__ sum_dz_xhat, bf16* __restrict__ dc, float* __restrict__ dgamma,
+                          float* __restrict__ dbeta, long long total8, int d, float inv_count, int training) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < d && dgamma) {  // parameter gradients once (first d threads of the grid; the host checks total8 >= d)
+    atomicAdd(dgamma + i, sum_dz_xhat[i]);
+    atomicAdd(dbeta + i, sum_dz[i]);
+  }
+  if (i >= total8) return;
+  const int ch = (int)((i * 8) % d);
+  float cv[8], dv[8], sc[8], sh[8], gm[8], rs[8], mu[8], s1[8], s2[8], o[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(c) + i), cv);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(ds) + i), dv);
+  ld8(scale + ch, sc); ld8(shift + ch, sh); ld8(gamma + ch, gm); ld8(rstd + ch, rs);
+  if (training) { ld8(mean + ch, mu); ld8(sum_dz + ch, s1); ld8(sum_dz_xhat + ch, s2); }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float n = bf16_round(fmaf(cv[k], sc[k], sh[k]));
+    const float dz = dv[k] * dsilu_f(n);
+    const float gr = gm[k] * rs[k];
+    if (training) {
+      const float xhat = (cv[k] - mu[k]) * rs[k];
+      o[k] = gr * (dz - s1[k] * inv_count - xhat * s2[k] * inv_count);
+    } else {
+      o[k] = gr * dz;
+    }
+  }
+  reinterpret_cast<uint4*>(dc)[i] = pack8(o);
+}
+
+// 8 du elements ↔ 16 interleaved (value, gate) elements of g / dg
+__global__ void __launch_bounds__(256)
+glu_bwd8_kernel(const bf16* __restrict__ du, const bf16* __restrict__ g, bf16* __restrict__ dg, long long total8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total8) return;
+  float dv[8], g0[8], g1[8], o0[8], o1[8];
+  unpack8(__ldg(reinterpret_cast<const uint4*>(du) + i), dv);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(g) + 2 * i), g0);
+  unpack8(__ldg(reinterpret_cast<const uint4*>(g) + 2 * i + 1), g1);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float s0 = sigmoid_f(g0[2 * k + 1]), s1 = sigmoid_f(g1[2 * k + 1]);
+    o0[2 * k] = dv[k] * s0;
+    o0[2 * k + 1] = dv[k] * g0[2 * k] * s0 * (1.f - s0);
+    o1[2 * k] = dv[4 + k] * s1;
+    o1[2 * k + 1] = dv[4 + k] * g1[2 * k] * s1 * (1.f - s1);
+  }
+  reinterpret_cast<uint4*>(dg)[2 * i] = pack8(o0);
+  reinterpret_cast<uint4*>(dg)[2 * i + 1] = pack8(o1);
+}
+
+// Time tiles per CTA so that the grid runs in as few "tile-times" as possible: waves(grid / resident slots) * tiles per CTA
+// (a grid of 1.15 waves costs two), most tiles per CTA (fewest weight reloads / gradient atomics) on ties.
+static int pick_tiles_per_cta(long long ctas_per_tile_row, int tiles, long long slots) {
+  int best = 1;
+  long long best_t = -1;
+  for (int tpc = 1; tpc <= tiles; ++tpc) {
+    const long long grid = ctas_per_tile_row * ((tiles + tpc - 1) / tpc);
+    const long long t = ((grid + slots - 1) / slots) * tpc;
+    if (best_t < 0 || t <= best_t) { best_t = t; best = tpc; }
+  }
+  return best;
+}
+
 template <int K>
 static int launch_dw_fwd(const bf16* u, const float* w, const float* bias, bf16* c, float* s, float* q, int B, int T,
                          int d, cudaStream_t st) {
   const int tiles = (T + kTT - 1) / kTT;
-  int tpc = 1;
   const int cb = (d + kCh - 1) / kCh;
-  while ((long long)cb * ((tiles + tpc - 1) / tpc) * B > (long long)num_sms() * 8 && tpc < tiles) ++tpc;
   const size_t smem = (size_t)(kTT + K - 1) * 128 * 4;
+  static int occ = 0;
+  if (!occ) B2C_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dwconv_fwd_kernel<K>, 128, smem));
+  const int tpc = pick_tiles_per_cta(cb * B, tiles, num_sms() * (occ > 0 ? occ : 1));
   dwconv_fwd_kernel<K><<<dim3(cb, (tiles + tpc - 1) / tpc, B), 128, smem, st>>>(u, w, bias, c, s, q, T, d, tpc);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
@@ -314,14 +420,13 @@ static int launch_dw_bwd(const bf16* dc, const bf16* u, const float* w, const in
                          float* db, int B, int T, int d, cudaStream_t st) {
   const int tiles = (T + kTT - 1) / kTT;
   const int cb = (d + kCh - 1) / kCh;
-  int tpc = 1;
-  while ((long long)cb * ((tiles + tpc - 1) / tpc) * B > (long long)num_sms() * 4 && tpc < tiles) ++tpc;
   const size_t smem = (size_t)(kTT + K - 1) * 128 * 4 * 2;
-  static bool set = false;
-  if (!set) {
+  static int occ = 0;
+  if (!occ) {
     B2C_CUDA(cudaFuncSetAttribute(dwconv_bwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    set = true;
+    B2C_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dwconv_bwd_kernel<K>, 128, smem));
   }
+  const int tpc = pick_tiles_per_cta(cb * B, tiles, num_sms() * (occ > 0 ? occ : 1));
   dwconv_bwd_kernel<K><<<dim3(cb, (tiles + tpc - 1) / tpc, B), 128, smem, st>>>(dc, u, w, len, du, dw, db, T, d, tpc);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
@@ -361,6 +466,13 @@ extern "C" int b2c_bn_silu_fwd(const void* c_bf16, const float* scale, const flo
                                int d, void* stream) {
   B2C_REQUIRE(d % 2 == 0, "bn_silu: d odd");
   const long long pairs = M * d / 2;
+  if (d % 8 == 0 && (reinterpret_cast<uintptr_t>(c_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(s_bf16) & 15) == 0) {
+    const long long n8 = M * d / 8;
+    bn_silu_fwd8_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const bf16*>(c_bf16), scale, shift, reinterpret_cast<bf16*>(s_bf16), n8, d);
+    B2C_LAUNCH_CHECK();
+    return B2C_OK;
+  }
   bn_silu_fwd_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const bf16*>(c_bf16), scale, shift, reinterpret_cast<bf16*>(s_bf16), pairs, d);
   B2C_LAUNCH_CHECK();
@@ -388,6 +500,15 @@ extern "C" int b2c_bn_silu_bwd_apply(const void* ds_bf16, const void* c_bf16, co
                                      int d, int training, void* stream) {
   const long long pairs = M * d / 2;
   B2C_REQUIRE(pairs >= d, "bn_silu_bwd_apply: tensor smaller than d");
+  if (d % 8 == 0 && M >= 8 && (reinterpret_cast<uintptr_t>(c_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(ds_bf16) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dc_bf16) & 15) == 0) {
+    const long long n8 = M * d / 8;  // >= d because M >= 8
+    bn_silu_bwd_apply8_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const bf16*>(ds_bf16), reinterpret_cast<const bf16*>(c_bf16), gamma, scale, shift, mean, rstd,
+        sum_dz, sum_dz_xhat, reinterpret_cast<bf16*>(dc_bf16), dgamma, dbeta, n8, d, 1.0f / (float)M, training);
+    B2C_LAUNCH_CHECK();
+    return B2C_OK;
+  }
   bn_silu_bwd_apply_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const bf16*>(ds_bf16), reinterpret_cast<const bf16*>(c_bf16), gamma, scale, shift, mean, rstd,
       sum_dz, sum_dz_xhat, reinterpret_cast<bf16*>(dc_bf16), dgamma, dbeta, pairs, d, 1.0f / (float)M, training);
@@ -413,6 +534,14 @@ extern "C" int b2c_dwconv_bwd(const void* dc_bf16, const void* u_bf16, const flo
 
 extern "C" int b2c_glu_bwd(const void* du_bf16, const void* g_bf16, void* dg_bf16, long long M, int d, void* stream) {
   const long long total = M * d;
+  if (total % 8 == 0 && (reinterpret_cast<uintptr_t>(du_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(g_bf16) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dg_bf16) & 15) == 0) {
+    glu_bwd8_kernel<<<(unsigned)((total / 8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const bf16*>(du_bf16), reinterpret_cast<const bf16*>(g_bf16), reinterpret_cast<bf16*>(dg_bf16),
+        total / 8);
+    B2C_LAUNCH_CHECK();
+    return B2C_OK;
+  }
   glu_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const bf16*>(du_bf16), reinterpret_cast<const bf16*>(g_bf16), reinterpret_cast<bf16*>(dg_bf16),
       total);
