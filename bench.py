@@ -226,16 +226,18 @@ def run_ours(args):
         loss.backward()
         fg.finish()
         opt.step()
-        return loss
+        # detached: a live `loss` keeps the autograd node — and with it this step's ~17 GB activation arena — alive into
+        # the next step.  That doubled the resident activations, and the first time it happened (timed step 2: the warm-up
+        # loop discards the return value) the caching allocator spent ~250 ms in device-synchronising cudaMallocs.
+        return loss.detach()
 
     per_step = []
     host_step = []
     in_flight = []
 
     def throttle(ev):
-        """The host may run at most two steps ahead of the GPU (the queue never drains, so nothing is lost): every step in
-        flight holds its own ~17 GB activation arena, and a host that gets a third step ahead makes the caching
-        allocator cudaMalloc another arena — a device-synchronising call that showed up as one 200-300 ms step."""
+        """The host may run at most two steps ahead of the GPU (the queue never drains, so nothing is lost); it bounds the
+        launch queue and the memory held by in-flight steps."""
         in_flight.append(ev)
         if len(in_flight) > 2:
             in_flight.pop(0).synchronize()
@@ -307,16 +309,6 @@ def run_ours(args):
         ev = torch.cuda.Event()
         ev.record()
         throttle(ev)
-    # Two more untimed steps that start from an idle, synchronised GPU exactly like the timed region does: only then does
-    # the host get a full step ahead of the device, a second ~17 GB activation arena becomes live, and the caching
-    # allocator has to cudaMalloc it (34 x 512 MiB, ~250 ms, device-synchronising).  In the first warm-up steps the host
-    # is slower than the GPU (first-launch costs, NCCL init), so that growth would otherwise land in timed step 2.
-    barrier()
-    for _ in range(2):
-        step(wav_dev, len_dev, False)
-        ev = torch.cuda.Event()
-        ev.record()
-        throttle(ev)
     ms, launches = timed(args.steps, False, sampler=clocks)
     clk = clocks.result() if rank == 0 else None
     step_ms_value = list(per_step)
@@ -344,7 +336,7 @@ def run_ours(args):
             "config": {"workload": f"Conformer-CTC-Large 18L d512 h8 k31 striding4x, {B}x30 s per GPU, mel+fwd+bwd+allreduce+AdamW",
                        "global_batch": world * B, "parallelism": f"dp{world}", "dropout": "0.1/0.1/att0.1",
                        "l2": "inputs+activations per step (>17 GB) exceed the 126 MB L2; no flush needed",
-                       "extra_untimed_steps_after_sync": 2, "step_ms": step_ms_value, "host_enqueue_ms": host_ms_value, "step_ms_e2e": step_ms_e2e,
+                       "step_ms": step_ms_value, "host_enqueue_ms": host_ms_value, "step_ms_e2e": step_ms_e2e,
                        "model_tflop_per_step_per_gpu": step_flops / 1e12,
                        "model_tflops_achieved_per_gpu": step_flops / (ms / args.steps / 1e3) / 1e12},
             "e2e": {"value": e2e, "unit": "audio-sec/s", "h2d_bytes_per_step": world * (wav_host.numel() * 4 + B * 8),
