@@ -527,6 +527,9 @@ class _EncoderFn(torch.autograd.Function):
     def backward(ctx, dout, _dlen):
         enc: B200ConformerEncoder = ctx.enc
         mt, W = ctx.meta, ctx.W
+        if ctx.S is None:
+            raise RuntimeError("B200ConformerEncoder: backward through the same graph a second time (activations are "
+                               "released after the first backward; retain_graph is not supported)")
         if dout is None:
             return (None,) * (3 + mt["nparams"])
         B, T, M = mt["B"], mt["T"], mt["M"]
@@ -695,6 +698,8 @@ class _EncoderFn(torch.autograd.Function):
                        G[f"pre_encode.conv.{ci}.weight"], G[f"pre_encode.conv.{ci}.bias"], B, Ts[s_i + 1], Fs[s_i + 1], C)
                 dyc = dxin
             conv1_bwd(dyc)
+        # the activations are dead now: drop them even if the caller keeps the loss (and with it this node) alive
+        ctx.S = ctx.layers_saved = ctx.arena = None
         if fg is not None:
             fg.ready(*fg.span("pre_encode."))
             return (None,) * (3 + len(plist))
