@@ -470,3 +470,27 @@ def test_stem_as_im2col_gemm_matches_the_stencil_kernels(B, F, T, C):
     L.gemm(dy, patches, C, 16, rows, C, 16, 1, 1, L.EPI_ACCUM_F32, out0=g16, ldo=16)
     report("stem_gemm_dw", g16[:, :9], dw_ref, 1e-2)
     report("stem_gemm_db", g16[:, 9], db_ref, 1e-2)
+
+
+@pytest.mark.parametrize("slope", [1.0, -1.0])
+def test_relpos_attention_scores_drifting_across_key_tiles(slope):
+    """The forward moves its softmax reference maximum lazily (from the PREVIOUS key tile's row maximum): logits that
+    climb (or fall) by ~20 nats per 64-key tile exercise the rescale path and the 2^(v - m_ref) >> 1 range."""
+    B, T, h, dk = 2, 600, 2, 64
+    d = h * dk
+    lengths = torch.tensor([T, 437], dtype=torch.int32, device=DEV)
+    qkvf = rnd(B, T, 3, h, dk, scale=1.0)
+    ramp = torch.linspace(0, 1, T, device=DEV) * 750.0 * slope  # (q0 ≈ 2) * ramp / sqrt(64): ~190 nats over 9.4 tiles
+    qkvf[:, :, 0, :, 0] = 2.0
+    qkvf[:, :, 1, :, 0] = ramp[None, :, None]
+    qkv16 = qkvf.reshape(B * T, 3 * d).to(torch.bfloat16)
+    pos16 = rnd(2 * T - 1, d, scale=1.0, seed=3).to(torch.bfloat16)
+    bu, bv = rnd(h, dk, scale=0.3, seed=4), rnd(h, dk, scale=0.3, seed=5)
+    ctx = torch.empty(B * T, d, dtype=torch.bfloat16, device=DEV)
+    ctx32 = torch.empty(B * T, d, device=DEV)
+    lse = torch.empty(B, h, T, device=DEV)
+    L.call("relpos_attn_fwd", qkv16, pos16, bu, bv, lengths, ctx, ctx32, lse, B, T, h, dk, 0.0, 0, 0)
+    q3 = qkv16.float().view(B, T, 3, h, dk)
+    ref = attn_reference(q3[:, :, 0], q3[:, :, 1], q3[:, :, 2], pos16.float().view(2 * T - 1, h, dk), bu, bv, lengths)
+    report(f"attn_fwd_drift_{slope:+.0f}", ctx32.view(B, T, d), ref, 2e-2)
+    report(f"attn_fwd_drift_bf16_{slope:+.0f}", ctx.view(B, T, d), ref, 2e-2)
