@@ -9,7 +9,6 @@ namespace b2c {
 
 constexpr int kTT = 32;         // output time steps per tile
 constexpr int kCh = 256;        // channels per CTA (128 threads x 2)
-constexpr int kMaxTaps = 31;
 
 // ------------------------------------------------------------------------------------------- forward
 template <int K>

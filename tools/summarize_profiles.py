@@ -116,9 +116,6 @@ def ncu_kernels():
 
 launches()
 ncu_kernels()
-ncu_raw("prof_gemm.ncu-rep", "ncu_gemm", "gemm")
-ncu_raw("prof_attn.ncu-rep", "ncu_attn", "attn")
-ncu_raw("prof_ln.ncu-rep", "ncu_ln_dwconv", "ln")
 for f in ("bench.log",):
     p = os.path.join(G, f)
     if os.path.exists(p):
