@@ -59,9 +59,9 @@ typedef struct {
   int rows_per_batch;     /* rows of the GEMM per batch item (T, or T*rows_inner) */
   int rows_inner;         /* RELU_MASK: rows per time step (F) */
   float alpha;
-  unsigned long long seed; /* dropout: Philox key */
+  unsigned long long seed; /* dropout: key of the stateless counter hash (element kept iff hash(seed, site, m*N+n) < keep) */
   unsigned int drop_site;  /* dropout: site id (layer*16 + site) */
-  unsigned int drop_keep;  /* dropout: 16-bit keep threshold = round((1-p)*65536), 0 = no dropout */
+  unsigned int drop_keep;  /* dropout: 16-bit keep threshold = round((1-p)*65536), 0 = no dropout; needs N % 16 == 0 */
   float drop_scale;        /* 1/(1-p) */
 } b2c_epilogue;
 

@@ -57,7 +57,11 @@ __device__ __forceinline__ float tanh_approx(float x) {
   return y;
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
-__device__ __forceinline__ float silu_f(float x) { return x * sigmoid_f(x); }
+// x * sigma(x) = h + h * tanh(h), h = x / 2: three instructions (FMUL, MUFU, FFMA)
+__device__ __forceinline__ float silu_f(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(h), h);
+}
 // d/dx silu(x) = s(1 + x(1-s))
 __device__ __forceinline__ float dsilu_f(float x) {
   float s = sigmoid_f(x);
@@ -324,7 +328,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// ---- Philox-4x32-10 counter RNG for dropout (stateless: fwd and bwd regenerate the same mask)
+// ---- Philox-4x32-10 counter RNG (mel dither; the dropout masks use the cheaper chunked hash below)
 __device__ __forceinline__ uint4 philox4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int i = 0; i < 10; ++i) {
