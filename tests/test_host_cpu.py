@@ -129,3 +129,25 @@ def test_bench_work_model_matches_baseline_md():
 
     assert abs(bench.flops_fwd_bwd(32, 751) / 1e12 - 27.34) < 0.02  # 27.34 TFLOP / step at 32x30 s
     assert abs(bench.flops_fwd_bwd(1, 751) / 6 / 1e9 * 2 - 298.47) < 12  # ~298.5 GFLOP fwd for 1x30 s (pos term is batch-indep.)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the oracle port timed on the host cores — the one other place besides tests / smoke
+    that may execute oracle/) prints ONE JSON line with the keys the driver reads, without touching a GPU."""
+    import json
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "audio-sec/s" and j["higher_is_better"] is True
+    for key in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config", "e2e",
+                "cpu_baseline"):
+        assert key in j, key
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["value"] == j["value"]
+    assert j["e2e"]["value"] == j["value"] and j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
+    assert j["value"] > 0
