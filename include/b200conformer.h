@@ -157,6 +157,12 @@ int b2c_relpos_attn_bwd(const void* qkv, const void* pos, const float* bias_u, c
                         int B, int T, int h, int dk, float drop_p, unsigned long long seed, unsigned int site,
                         void* stream);
 
+/* SpecAugment applied in one pass (spectr_augment.py:135-215, SURVEY §8f "next"): out[b,f,t] = mask_value inside any of
+ * the utterance's n_t time spans [t_start, t_end) or n_f frequency bands [f_start, f_end) (arrays [B,n_t] / [B,n_f] i32,
+ * drawn by the host module with the reference's own random draws), else in[b,f,t].  in may equal out. */
+int b2c_spec_augment(const float* in, float* out, const int32_t* t_start, const int32_t* t_end, const int32_t* f_start,
+                     const int32_t* f_end, int B, int F, int T, int n_t, int n_f, float mask_value, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ subsampling
  * First Conv2d(1→C, 3x3, stride 2, pad 1) + bias + ReLU + time masks, channels-last output [B, T1, F1, C] bf16
  * (subsampling.py:217-253,725-753).  mel [B, F, T] f32 (the encoder's input layout), w [C,1,3,3] f32,

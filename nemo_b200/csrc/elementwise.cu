@@ -227,6 +227,31 @@ __global__ void scale_drop_cast_kernel(const float* __restrict__ in, bf16* __res
   out[i] = __float2bfloat16_rn(v);
 }
 
+// SpecAugment (spectr_augment.py:135-215): out[b,f,t] = mask_value where t falls in one of the utterance's n_t time spans
+// or f in one of its n_f frequency bands, else in[b,f,t].  One pass; the reference builds [B,n,axis] mask tensors and runs
+// two masked_fill passes.  Span bounds come from the host module (same random draws as the reference).
+__global__ void __launch_bounds__(256)
+spec_augment_kernel(const float* __restrict__ in, float* __restrict__ out, const int32_t* __restrict__ t_start,
+                    const int32_t* __restrict__ t_end, const int32_t* __restrict__ f_start, const int32_t* __restrict__ f_end,
+                    int F, int T, int n_t, int n_f, float mask_value) {
+  extern __shared__ int32_t sb[];  // [2*n_t] time spans, [2*n_f] frequency bands of this utterance
+  const int b = blockIdx.z, f = blockIdx.y;
+  for (int i = threadIdx.x; i < n_t; i += blockDim.x) { sb[2 * i] = t_start[b * n_t + i]; sb[2 * i + 1] = t_end[b * n_t + i]; }
+  for (int i = threadIdx.x; i < n_f; i += blockDim.x) {
+    sb[2 * n_t + 2 * i] = f_start[b * n_f + i];
+    sb[2 * n_t + 2 * i + 1] = f_end[b * n_f + i];
+  }
+  __syncthreads();
+  bool fmask = false;
+  for (int i = 0; i < n_f; ++i) fmask |= (f >= sb[2 * n_t + 2 * i] && f < sb[2 * n_t + 2 * i + 1]);
+  const size_t row = ((size_t)b * F + f) * T;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    bool m = fmask;
+    for (int i = 0; i < n_t; ++i) m |= (t >= sb[2 * i] && t < sb[2 * i + 1]);
+    out[row + t] = m ? mask_value : in[row + t];
+  }
+}
+
 // in [A,B,C] → out; mode 0: out[b][a][c] (swap dims 0,1); mode 1: out[a][c][b] (swap dims 1,2)
 template <typename TO, bool ACCUM>
 __global__ void permute3_kernel(const float* __restrict__ in, TO* __restrict__ out, int A, int B, int C, int mode) {
@@ -471,6 +496,17 @@ extern "C" int b2c_log_softmax_bwd(const float* dlogp, const float* logp, void* 
   B2C_REQUIRE(M > 0 && V > 0 && ld >= V, "log_softmax_bwd: bad args");
   log_softmax_bwd_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(dlogp, logp, reinterpret_cast<bf16*>(dlogits_bf16),
                                                                          ld, M, V);
+  B2C_LAUNCH_CHECK();
+  return B2C_OK;
+}
+
+extern "C" int b2c_spec_augment(const float* in, float* out, const int32_t* t_start, const int32_t* t_end,
+                                const int32_t* f_start, const int32_t* f_end, int B, int F, int T, int n_t, int n_f,
+                                float mask_value, void* stream) {
+  B2C_REQUIRE(B > 0 && F > 0 && T > 0 && n_t >= 0 && n_f >= 0 && n_t + n_f <= 4096, "spec_augment: bad shape");
+  const int tb = (T + 255) / 256;
+  spec_augment_kernel<<<dim3(tb < 8 ? tb : 8, F, B), 256, 2 * (n_t + n_f) * sizeof(int32_t), (cudaStream_t)stream>>>(
+      in, out, t_start, t_end, f_start, f_end, F, T, n_t, n_f, mask_value);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
 }

@@ -331,6 +331,49 @@ def ctc_head(sd, x: torch.Tensor, prefix="decoder_layers.0."):
 
 
 # ----------------------------------------------------------------------------------------------
+# SpecAugment (training-time masking between the front-end and the encoder)
+# ----------------------------------------------------------------------------------------------
+def spec_augment_vectorized(spec: torch.Tensor, length: torch.Tensor, freq_masks: int, time_masks: int, freq_width: int,
+                            time_width, mask_value: float = 0.0) -> torch.Tensor:
+    """SpecAugment._forward_vectorized / _apply_masks (spectr_augment.py:135-215): time masks first, then frequency
+    masks; per axis one `torch.rand` draw for the widths and one for the starts (device RNG of `spec`)."""
+
+    def apply(x, num_masks, width, axis):
+        B, n = x.shape[0], x.shape[axis]
+        if axis == 2 and isinstance(width, float):
+            width = torch.clamp(width * length, max=n).unsqueeze(1)
+        w = (torch.rand((B, num_masks), device=x.device, dtype=torch.float32) * width).long()
+        st = torch.rand((B, num_masks), device=x.device, dtype=torch.float32)
+        st = (st * ((length.unsqueeze(1) if axis == 2 else n) - w)).long()
+        idx = torch.arange(n, device=x.device)
+        m = ((idx >= st.unsqueeze(-1)) & (idx < (st + w).unsqueeze(-1))).any(dim=1)
+        m = m[:, None, :] if axis == 2 else m[:, :, None]
+        return x.masked_fill(m.expand_as(x), mask_value)
+
+    return apply(apply(spec, time_masks, time_width, 2), freq_masks, freq_width, 1)
+
+
+def spec_augment_legacy(spec: torch.Tensor, length: torch.Tensor, rng, freq_masks: int, time_masks: int, freq_width: int,
+                        time_width, mask_value: float = 0.0) -> torch.Tensor:
+    """SpecAugment._forward_legacy (spectr_augment.py:102-133): host `random.Random` draws per utterance."""
+    B, F, _ = spec.shape
+    lens = length.cpu().numpy()
+    mask = torch.zeros(spec.shape, dtype=torch.bool)
+    for b in range(B):
+        for _ in range(freq_masks):
+            st = rng.randint(0, F - freq_width)
+            w = rng.randint(0, freq_width)
+            mask[b, st:st + w, :] = True
+        tmax = max(1, int(lens[b] * time_width)) if not isinstance(time_width, int) else time_width
+        hi = max(1, lens[b] - tmax)
+        for _ in range(time_masks):
+            st = rng.randint(0, hi)
+            w = rng.randint(0, tmax)
+            mask[b, :, st:st + w] = True
+    return spec.masked_fill(mask.to(spec.device), mask_value)
+
+
+# ----------------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md §8d)
 # ----------------------------------------------------------------------------------------------
 def synthetic_waveforms(batch: int, seconds: float, seed=1234, sample_rate=16000, ragged=False):

@@ -494,3 +494,29 @@ def test_relpos_attention_scores_drifting_across_key_tiles(slope):
     ref = attn_reference(q3[:, :, 0], q3[:, :, 1], q3[:, :, 2], pos16.float().view(2 * T - 1, h, dk), bu, bv, lengths)
     report(f"attn_fwd_drift_{slope:+.0f}", ctx32.view(B, T, d), ref, 2e-2)
     report(f"attn_fwd_drift_bf16_{slope:+.0f}", ctx.view(B, T, d), ref, 2e-2)
+
+
+@pytest.mark.parametrize("time_width", [10, 0.05])
+def test_spec_augment_module_matches_the_oracle(time_width):
+    """B200SpecAugment (one CUDA pass) against the oracle restatement of the reference class under the same RNG state:
+    bit-identical output in the vectorised (device RNG) and the legacy (host RNG) modes."""
+    import random
+
+    from nemo_b200.spec_augment import B200SpecAugment
+    from oracle import conformer_oracle as O
+
+    x = rnd(3, 80, 301)
+    ln = torch.tensor([301, 250, 17], device=DEV)
+    sa = B200SpecAugment(freq_masks=2, time_masks=5, freq_width=27, time_width=time_width, mask_value=0.0)
+    torch.manual_seed(11)
+    got = sa(input_spec=x, length=ln)
+    torch.manual_seed(11)
+    want = O.spec_augment_vectorized(x, ln, 2, 5, 27, time_width)
+    assert torch.equal(got, want) and 0.05 < (got == 0).float().mean().item() < 0.9
+    sa = B200SpecAugment(freq_masks=2, time_masks=5, freq_width=27, time_width=time_width, rng=random.Random(5),
+                         mask_value=-1.5, use_vectorized_code=False)
+    got = sa(input_spec=x, length=ln)
+    want = O.spec_augment_legacy(x, ln, random.Random(5), 2, 5, 27, time_width, mask_value=-1.5)
+    assert torch.equal(got, want)
+    # no masks at all: identity
+    assert torch.equal(B200SpecAugment()(input_spec=x, length=ln), x)

@@ -113,3 +113,23 @@ def test_init_state_dict_layout_matches_reference():
         assert set(sd) == set(ref_sd)
         for k in sd:
             assert tuple(sd[k].shape) == tuple(ref_sd[k].shape), k
+
+
+@needs_ref
+@pytest.mark.parametrize("time_width", [10, 0.05])
+def test_live_reference_spec_augment(time_width):
+    """oracle restatement of SpecAugment (both RNG modes) against the exec'd reference class: identical masks."""
+    import random
+
+    ref = rl.load()
+    x = torch.randn(3, 80, 301)
+    ln = torch.tensor([301, 250, 17])
+    sa = ref.SpecAugment(freq_masks=2, time_masks=5, freq_width=27, time_width=time_width, use_vectorized_code=True)
+    torch.manual_seed(7)
+    want = sa(input_spec=x, length=ln)
+    torch.manual_seed(7)
+    got = O.spec_augment_vectorized(x, ln, 2, 5, 27, time_width)
+    assert torch.equal(want, got) and 0.05 < (got == 0).float().mean() < 0.9
+    sa = ref.SpecAugment(freq_masks=2, time_masks=5, freq_width=27, time_width=time_width, rng=random.Random(3),
+                         use_vectorized_code=False)
+    assert torch.equal(sa(input_spec=x, length=ln), O.spec_augment_legacy(x, ln, random.Random(3), 2, 5, 27, time_width))
