@@ -133,3 +133,17 @@ def test_live_reference_spec_augment(time_width):
     sa = ref.SpecAugment(freq_masks=2, time_masks=5, freq_width=27, time_width=time_width, rng=random.Random(3),
                          use_vectorized_code=False)
     assert torch.equal(sa(input_spec=x, length=ln), O.spec_augment_legacy(x, ln, random.Random(3), 2, 5, 27, time_width))
+
+
+@pytest.mark.parametrize("tag,time_width", [("int", 10), ("adaptive", 0.05)])
+def test_golden_spec_augment(golden_dir, tag, time_width):
+    """masks produced by the reference's SpecAugment (tools/make_golden.py) vs the oracle restatement, both RNG modes"""
+    import random
+
+    z = np.load(os.path.join(golden_dir, "spec_augment.npz"))
+    x, ln = torch.from_numpy(z["x"]), torch.from_numpy(z["length"])
+    torch.manual_seed(7)
+    got = O.spec_augment_vectorized(x, ln, 2, 5, 27, time_width)
+    assert np.array_equal((got == 0).numpy(), z[f"vec_{tag}"])
+    got = O.spec_augment_legacy(x, ln, random.Random(3), 2, 5, 27, time_width)
+    assert np.array_equal((got == 0).numpy(), z[f"legacy_{tag}"])

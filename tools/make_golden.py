@@ -64,6 +64,27 @@ def gen_encoder(name, **kw):
                         loss=loss.detach().numpy(), r=r.numpy(), **sd_np(sd0), **grads, **bn)
 
 
+def gen_spec_augment():
+    """SpecAugment of the reference in both RNG modes: the masks depend only on torch's CPU generator (vectorised mode,
+    manual_seed 7) or on random.Random(3) (legacy mode) — both reproducible anywhere."""
+    import random
+
+    ref = rl.load()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 80, 301, generator=g)
+    length = torch.tensor([301, 250, 17])
+    out = {"x": x.numpy(), "length": length.numpy()}
+    for tag, tw in (("int", 10), ("adaptive", 0.05)):
+        sa = ref.SpecAugment(freq_masks=2, time_masks=5, freq_width=27, time_width=tw, use_vectorized_code=True)
+        torch.manual_seed(7)
+        out[f"vec_{tag}"] = (sa(input_spec=x, length=length) == 0).numpy()
+        sa = ref.SpecAugment(freq_masks=2, time_masks=5, freq_width=27, time_width=tw, rng=random.Random(3),
+                             use_vectorized_code=False)
+        out[f"legacy_{tag}"] = (sa(input_spec=x, length=length) == 0).numpy()
+    np.savez_compressed(os.path.join(OUT, "spec_augment.npz"), **out)
+    print("spec_augment.npz", {k: (v.shape, float(v.mean())) for k, v in out.items() if k not in ("x", "length")})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_mel()
@@ -117,3 +138,4 @@ if __name__ == "__main__":
     gen_encoder_cuda_cfg()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
+    gen_spec_augment()
