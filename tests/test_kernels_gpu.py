@@ -520,3 +520,39 @@ def test_spec_augment_module_matches_the_oracle(time_width):
     assert torch.equal(got, want)
     # no masks at all: identity
     assert torch.equal(B200SpecAugment()(input_spec=x, length=ln), x)
+
+
+def test_gemm_epilogues_on_odd_tile_counts_narrow_n_and_shared_dropout_masks():
+    """3 row tiles (the CTA pair's second tile of the last pair is a dummy), N = 384 (128-wide tiles, 3 of them), ragged
+    K; the SiLU forward and the SiLU' backward epilogues must drop exactly the same elements for the same (seed, site)."""
+    M, N, K, p = 333, 384, 200, 0.2
+    A, B, bias = rnd(M, K, dtype=torch.bfloat16), rnd(N, K, scale=0.08, dtype=torch.bfloat16), rnd(N)
+    z = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    h = torch.empty_like(z)
+    L.gemm(A, B, M, N, K, K, K, 0, 0, L.EPI_SILU, out0=z, out1=h, bias=bias, seed=9, drop_site=21, drop_p=p)
+    zr = A.float() @ B.float().T + bias
+    report("silu_z_odd", z, zr, 1e-2)
+    h_full = torch.nn.functional.silu(z.float()).to(torch.bfloat16).float()
+    kept = h.float() != 0
+    frac = (kept | (h_full == 0)).float().mean().item()
+    print("keep fraction", frac)
+    assert abs(frac - (1 - p)) < 0.01
+    assert torch.allclose(h.float()[kept], (h_full / (1 - p))[kept], rtol=1e-2, atol=1e-3)
+    G, W = rnd(M, K, seed=5, dtype=torch.bfloat16), rnd(N, K, scale=0.08, seed=6, dtype=torch.bfloat16)
+    dz = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    L.gemm(G, W, M, N, K, K, K, 0, 0, L.EPI_DSILU, out0=dz, aux=z, seed=9, drop_site=21, drop_p=p)
+    zf = z.float()
+    s = torch.sigmoid(zf)
+    full = (G.float() @ W.float().T).to(torch.bfloat16).float() * (s * (1 + zf * (1 - s))) / (1 - p)
+    mask = kept | (h_full == 0)  # elements the forward kept (h_full == 0 cannot tell; treat as kept and compare loosely)
+    report("dsilu_odd_kept", dz.float() * kept, full * kept, 1.5e-2)
+    dropped = ~mask
+    assert dz.float()[dropped].abs().max().item() == 0.0
+    # plain bf16 and the fp32 residual epilogue on the same shape
+    o = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    L.gemm(A, B, M, N, K, K, K, 0, 0, L.EPI_BF16, out0=o, bias=bias)
+    report("bf16_odd", o, zr, 1e-2)
+    x = rnd(M, N)
+    r = torch.empty_like(x)
+    L.gemm(A, B, M, N, K, K, K, 0, 0, L.EPI_RESID_F32, out0=r, aux=x, bias=bias, alpha=0.5)
+    report("resid_odd", r, x + 0.5 * zr, 5e-3)
