@@ -151,3 +151,37 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["value"] == j["value"]
     assert j["e2e"]["value"] == j["value"] and j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
     assert j["value"] > 0
+
+
+@pytest.mark.parametrize("time_width", [10, 0.05])
+def test_spec_augment_host_draws_match_the_oracle(time_width):
+    """the span boundaries B200SpecAugment hands to its CUDA kernel (host logic, no GPU needed) reproduce the masks of the
+    oracle restatement of the reference class, in the device-RNG and in the host-RNG mode"""
+    import random
+
+    from nemo_b200.spec_augment import B200SpecAugment
+
+    B, F, T = 3, 80, 301
+    x = torch.randn(B, F, T)
+    ln = torch.tensor([301, 250, 17])
+
+    def mask_from(t0, t1, f0, f1):
+        t, f = torch.arange(T), torch.arange(F)
+        mt = ((t[None, None, :] >= t0[:, :, None]) & (t[None, None, :] < t1[:, :, None])).any(1)
+        mf = ((f[None, None, :] >= f0[:, :, None]) & (f[None, None, :] < f1[:, :, None])).any(1)
+        return mt[:, None, :] | mf[:, :, None]
+
+    sa = B200SpecAugment(freq_masks=2, time_masks=5, freq_width=27, time_width=time_width)
+    torch.manual_seed(7)
+    t0, t1 = sa._bounds_vectorized(B, T, 5, ln, time_width, sa.TIME_AXIS, x.device)
+    f0, f1 = sa._bounds_vectorized(B, F, 2, ln, 27, sa.FREQ_AXIS, x.device)
+    torch.manual_seed(7)
+    want = O.spec_augment_vectorized(x, ln, 2, 5, 27, time_width) == 0
+    assert torch.equal(mask_from(t0, t1, f0, f1), want)
+
+    sa = B200SpecAugment(freq_masks=2, time_masks=5, freq_width=27, time_width=time_width, rng=random.Random(3),
+                         use_vectorized_code=False)
+    fs, fe, ts, te = sa._bounds_legacy(B, F, ln.numpy())
+    want = O.spec_augment_legacy(x, ln, random.Random(3), 2, 5, 27, time_width) == 0
+    got = mask_from(torch.tensor(ts), torch.tensor(te), torch.tensor(fs), torch.tensor(fe))
+    assert torch.equal(got, want)
