@@ -31,3 +31,20 @@ def test_argument_validation_does_not_need_a_gpu():
     e = _lib.Epilogue()
     rc = _lib.lib.b2c_gemm(None, None, 0, 0, 0, 0, 0, 0, 0, 0, ctypes.byref(e), None)
     assert rc == -1 and "bad shape" in _lib.last_error()
+
+
+def test_more_argument_validation_without_a_gpu():
+    """error behaviour of the entry points added this round: a negative return code + a message, before any CUDA call"""
+    from nemo_b200 import _lib
+
+    # dropout epilogues need N % 16 == 0 (one hash chunk per 16 output columns)
+    e = _lib.Epilogue()
+    e.out0 = ctypes.c_void_p(16)
+    e.drop_keep = 59000
+    rc = _lib.lib.b2c_gemm(ctypes.c_void_p(16), ctypes.c_void_p(16), 128, 24, 64, 64, 64, 0, 0, 0, ctypes.byref(e), None)
+    assert rc < 0 and "N % 16" in _lib.last_error()
+    rc = _lib.lib.b2c_spec_augment(None, None, None, None, None, None, 0, 80, 100, 1, 1, ctypes.c_float(0.0), None)
+    assert rc < 0 and "spec_augment" in _lib.last_error()
+    rc = _lib.lib.b2c_subsample_im2col(None, None, None, 0, 80, 100, None)
+    assert rc < 0 and "im2col" in _lib.last_error()
+    assert _lib.lib.b2c_launch_count() == 0  # nothing was launched
