@@ -1,18 +1,23 @@
 #!/usr/bin/env python
-"""bench.py — audio-seconds/s of the Conformer-ASR encoder hot path (mel front-end → subsampling → 18 Conformer
-layers, forward + backward + gradient all-reduce + AdamW) on N B200s.
+"""bench.py — audio-seconds/s of the Conformer-ASR encoder hot path (mel front-end → subsampling → Conformer layers,
+forward + backward + gradient all-reduce + AdamW/Noam) on N B200s, for every BASELINE.json configuration.
 
-Workload = BASELINE.json configs[1]: Conformer-CTC-Large (18L, d=512, 8 heads, conv k=31, striding 4x), fwd+bwd,
-32 x 30 s synthetic 16 kHz utterances PER GPU (weak scaling), bf16 tensor-core arithmetic with fp32 master weights,
-dropout active (0.1 / 0.1 / att 0.1 as in examples/asr/conf/conformer/conformer_ctc_bpe.yaml), random-init weights.
+    python bench.py [--gpus N] [--steps K] [--warmup W]              # configs[1], the driver's headline (default)
+    python bench.py --config 3|4 [--scaling weak|strong] ...         # configs[2] (FastConformer-L) / configs[3] (Transducer-XL)
+    python bench.py --config 5                                       # configs[4]: mel preprocessor sweep (HBM roofline)
+    python bench.py --impl reference [--config C] [--steps K]        # the reference algorithm on the host CPU cores
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # ours (N>1: launched under torchrun)
-    python bench.py --impl reference [--steps K] [--warmup W]      # the reference algorithm on the host CPU cores
+  --config 2  Conformer-CTC-Large   18L d512  h8 k31 striding 4x  C=512   32 x 30 s per GPU (1 GPU: the quoted metric)
+  --config 3  FastConformer-Large   17L d512  h8 k9  dw_striding 8x C=256 16 x 30 s per GPU (64 x 30 s over 4 GPUs)
+  --config 4  Conformer-Transd.-XL  24L d1024 h8 k5  striding 4x  C=1024   2 x 30 s per GPU (16 x 30 s over 8 GPUs)
+  --config 5  AudioToMelSpectrogramPreprocessor sweep: 1-60 s x batch 1-256, forward only
 
 Prints ONE JSON line (contract in the task statement): value = whole-job audio-s/s with inputs resident in HBM;
-e2e = same metric through the public module API with pinned-host inputs (H2D each step) and a D2H loss read;
-roofline = achieved TFLOP/s of the dominant kernel family (tcgen05 GEMM) from CUDA events, vs the measured bf16 peak;
-cpu_baseline = the fp32 oracle port timed on this box's host cores on a bounded sample.
+e2e = same metric through the public module API with pinned-host inputs (H2D each step) and a D2H result read;
+roofline = achieved TFLOP/s of the dominant kernel family (tcgen05 GEMM) from CUDA events vs the measured bf16 peak
+(config 5: achieved algorithmic GB/s of the mel kernels vs the measured HBM peak); cpu_baseline = the fp32 oracle port on
+this box's host cores on a bounded sample; gpu_eager_baseline = the reference op sequence (oracle port) on this B200 under
+torch.autocast(bf16), materialised attention and `use_pytorch_sdpa` variants (SURVEY.md §8d "the number to beat").
 """
 from __future__ import annotations
 
@@ -20,9 +25,8 @@ import argparse
 import gc
 import json
 import os
-import subprocess
+import platform
 import sys
-import threading
 import time
 
 import torch
@@ -30,18 +34,59 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-LARGE = dict(n_layers=18, d_model=512, n_heads=8, conv_kernel_size=31, subsampling_kind="striding", subsampling_factor=4)
-SECS, SR, PER_GPU_BATCH = 30.0, 16000, 32
+SECS, SR = 30.0, 16000
+CONFIGS = {
+    2: dict(name="Conformer-CTC-Large", tag="18L d512 h8 k31 striding4x C512", per_gpu_batch=32, ref_gpus=1,
+            model=dict(n_layers=18, d_model=512, n_heads=8, conv_kernel_size=31, subsampling_kind="striding",
+                       subsampling_factor=4, subsampling_conv_channels=512)),
+    3: dict(name="FastConformer-Large", tag="17L d512 h8 k9 dw_striding8x C256", per_gpu_batch=16, ref_gpus=4,
+            model=dict(n_layers=17, d_model=512, n_heads=8, conv_kernel_size=9, subsampling_kind="dw_striding",
+                       subsampling_factor=8, subsampling_conv_channels=256)),
+    4: dict(name="Conformer-Transducer-XL", tag="24L d1024 h8 k5 striding4x C1024", per_gpu_batch=2, ref_gpus=8,
+            model=dict(n_layers=24, d_model=1024, n_heads=8, conv_kernel_size=5, subsampling_kind="striding",
+                       subsampling_factor=4, subsampling_conv_channels=1024)),
+}
+LARGE = CONFIGS[2]["model"]
 METRIC = "audio-sec/s Conformer-L fwd+bwd"
+METRICS = {2: METRIC, 3: "audio-sec/s FastConformer-L fwd+bwd", 4: "audio-sec/s Conformer-Transducer-XL encoder fwd+bwd",
+           5: "audio-sec/s AudioToMelSpectrogramPreprocessor fwd"}
+SWEEP_SECS = (1, 5, 10, 30, 60)
+SWEEP_BATCH = (1, 8, 32, 128, 256)
 
 
-def flops_fwd_bwd(B, T, d=512, L=18, h=8, dff=2048, k=31, C=512, F1=40, F2=20, T1=1501):
-    """dense-contraction MACs of the forward x 6 (fwd + bwd = 3 x 2 x MAC)."""
+def enc_frames(S, factor):
+    t = S // 160 + 1
+    for _ in range({4: 2, 8: 3}[factor]):
+        t = (t - 1) // 2 + 1
+    return t
+
+
+def flops_fwd_bwd(B, T=None, d=512, L=18, h=8, dff=None, k=31, C=None, kind="striding", factor=4, S=int(SECS * SR), feat=80, **_):
+    """dense-contraction MACs of the forward x 6 (fwd + bwd = 3 x 2 x MAC), any BASELINE config."""
+    dff = dff or 4 * d
+    C = C or d
     dk = d // h
-    sub = B * T1 * F1 * C * 9 + B * T * F2 * C * C * 9 + B * T * F2 * C * d
+    Ts, Fs = [S // 160 + 1], [feat]
+    for _ in range({4: 2, 8: 3}[factor]):
+        Ts.append((Ts[-1] - 1) // 2 + 1)
+        Fs.append((Fs[-1] - 1) // 2 + 1)
+    T = T or Ts[-1]
+    if kind == "striding":
+        sub = B * Ts[1] * Fs[1] * C * 9 + B * Ts[2] * Fs[2] * C * C * 9 + B * Ts[2] * Fs[2] * C * d
+    else:
+        sub = B * Ts[1] * Fs[1] * C * 9
+        for i in (2, 3):
+            sub += B * Ts[i] * Fs[i] * C * 9 + B * Ts[i] * Fs[i] * C * C
+        sub += B * Ts[3] * Fs[3] * C * d
     per_layer = (4 * B * T * d * dff + 4 * B * T * d * d + (2 * T - 1) * d * d + B * h * T * T * dk
                  + B * h * T * (2 * T - 1) * dk + B * h * T * T * dk + 2 * B * T * d * d + B * T * d * k + B * T * d * d)
     return 6.0 * (sub + L * per_layer)
+
+
+def model_flops(cfg_id, B):
+    m = CONFIGS[cfg_id]["model"]
+    return flops_fwd_bwd(B, d=m["d_model"], L=m["n_layers"], h=m["n_heads"], k=m["conv_kernel_size"],
+                         C=m["subsampling_conv_channels"], kind=m["subsampling_kind"], factor=m["subsampling_factor"])
 
 
 def measured_peaks():
@@ -53,6 +98,16 @@ def measured_peaks():
         except Exception:
             pass
     return dict(tflops=1590.0, hbm=6650.0, src="fallback")
+
+
+def ncu_traffic(key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
+    `ncu --set full` capture (profiles/dram_traffic.json, written by tools/summarize_profiles.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    try:
+        return json.load(open(p)).get(key)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -110,13 +165,16 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference / CPU arm
-def cpu_reference_step(O, sd, wav, wlen, cfg):
+def oracle_kwargs(m):
+    return dict(n_layers=m["n_layers"], d_model=m["d_model"], n_heads=m["n_heads"], subsampling_kind=m["subsampling_kind"],
+                subsampling_factor=m["subsampling_factor"])
+
+
+def cpu_reference_step(O, sd, wav, wlen, m):
     """One fwd+bwd of the reference algorithm (fp32 oracle port, PyTorch eager on the host cores)."""
     params = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and "running" not in k) else v) for k, v in sd.items()}
     mel, mlen = O.mel_frontend(wav, wlen)
-    y, _ = O.encoder_forward(params, mel, mlen, n_layers=cfg["n_layers"], d_model=cfg["d_model"], n_heads=cfg["n_heads"],
-                             subsampling_kind=cfg["subsampling_kind"], subsampling_factor=cfg["subsampling_factor"],
-                             training=True)
+    y, _ = O.encoder_forward(params, mel, mlen, training=True, **oracle_kwargs(m))
     (y.float().pow(2).mean()).backward()
 
 
@@ -130,38 +188,248 @@ def host_threads():
     return max(1, min(n, 32))
 
 
-def cpu_baseline(steps=2, warmup=1, batch=1, secs=10.0):
+def host_info():
+    model = platform.processor() or ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    return {"cpu": model, "logical_cpus": os.cpu_count(), "threads_used": host_threads()}
+
+
+def cpu_baseline(cfg_id=2, steps=2, warmup=1, batch=1, secs=SECS):
+    """The reference algorithm on the host cores, 1 x 30 s utterance per step (B=1 x 30 s, scale linearly)."""
     from oracle import conformer_oracle as O
     torch.set_num_threads(host_threads())
-    sd = O.init_state_dict(seed=0, **LARGE)
+    if cfg_id == 5:
+        wav, wlen = O.synthetic_waveforms(32, secs)
+        for _ in range(warmup):
+            O.mel_frontend(wav, wlen)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.mel_frontend(wav, wlen)
+        dt = (time.perf_counter() - t0) / steps
+        return {"value": 32 * secs / dt, "unit": "audio-sec/s", "cores": torch.get_num_threads(), "kind": "port",
+                "sample": f"{steps} passes of 32x{int(secs)} s through the fp32 oracle port of FilterbankFeatures.forward "
+                          f"(torch.stft + mel + log + normalise, PyTorch eager, {torch.get_num_threads()} threads)",
+                "ms_per_step": dt * 1e3, "host": host_info()}
+    m = CONFIGS[cfg_id]["model"]
+    sd = O.init_state_dict(seed=0, **{k: v for k, v in m.items()})
     wav, wlen = O.synthetic_waveforms(batch, secs)
     for _ in range(warmup):
-        cpu_reference_step(O, sd, wav, wlen, LARGE)
+        cpu_reference_step(O, sd, wav, wlen, m)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_reference_step(O, sd, wav, wlen, LARGE)
+        cpu_reference_step(O, sd, wav, wlen, m)
     dt = (time.perf_counter() - t0) / steps
     return {"value": batch * secs / dt, "unit": "audio-sec/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} steps of {batch}x{int(secs)} s mel+fwd+bwd, Conformer-CTC-Large (fp32 oracle port of the reference "
-                      f"modules, PyTorch eager, {torch.get_num_threads()} threads)",
-            "ms_per_step": dt * 1e3}
+            "sample": f"{steps} steps of {batch}x{int(secs)} s mel+fwd+bwd, {CONFIGS[cfg_id]['name']} (fp32 oracle port of the "
+                      f"reference modules, PyTorch eager, {torch.get_num_threads()} threads)",
+            "ms_per_step": dt * 1e3, "host": host_info()}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline(steps=max(1, args.steps), warmup=max(1, min(args.warmup, 1)), batch=1)
+    c = args.config
+    # bounded: each step is one 1x30 s utterance (≈2-4 s of CPU work for Large, ≈15 s for XL)
+    steps = max(1, min(args.steps, 5 if c != 4 else 2))
+    cb = cpu_baseline(cfg_id=c, steps=steps, warmup=1, batch=1)
+    name = "AudioToMelSpectrogramPreprocessor" if c == 5 else f"{CONFIGS[c]['name']} {CONFIGS[c]['tag']}"
     out = {
-        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "audio-sec/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "impl": "reference", "metric": METRICS[c], "value": cb["value"], "unit": "audio-sec/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Conformer-CTC-Large 18L d512 h8 k31 striding4x fwd+bwd, 30 s utterances",
-                   "sample": "1x10 s utterance per step on host CPU cores"},
+        "config": {"workload": f"{name} {'fwd' if c == 5 else 'fwd+bwd'}, 30 s utterances",
+                   "sample": ("32x30 s per step" if c == 5 else "1x30 s utterance per step") + " on host CPU cores",
+                   "host": cb["host"]},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "audio-sec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU eager baseline
+def gpu_eager_baseline(cfg_id, dev, batch_try=(16, 8, 4, 2, 1), steps=2):
+    """SURVEY.md §8(d) secondary baseline: the reference op sequence (oracle port: F.conv2d / F.linear / matmul /
+    softmax / layer_norm ... exactly the reference's torch calls) on THIS GPU under torch.autocast(bf16), fwd+bwd, default
+    materialised attention and the `use_pytorch_sdpa=True` branch.  Batch is the largest of batch_try that fits (the
+    materialised [B,h,T,2T-1] score tensors of 18-24 layers do not fit 32 x 30 s in 180 GB); audio-s/s is per-GPU."""
+    from oracle import conformer_oracle as O
+    m = CONFIGS[cfg_id]["model"]
+    sd = {k: v.to(dev) for k, v in O.init_state_dict(seed=0, **m).items()}
+    out = {"unit": "audio-sec/s", "what": "oracle port of the reference modules, torch eager on this GPU, autocast bf16, fwd+bwd"}
+
+    def one(B, sdpa):
+        wav, wlen = O.synthetic_waveforms(B, SECS)
+        wav, wlen = wav.to(dev), wlen.to(dev)
+
+        def step():
+            params = {k: (v.detach().requires_grad_(True) if (v.is_floating_point() and "running" not in k) else v) for k, v in sd.items()}
+            with torch.no_grad():
+                mel, mlen = O.mel_frontend(wav, wlen)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y, _ = O.encoder_forward(params, mel, mlen, training=True, use_sdpa=sdpa, **oracle_kwargs(m))
+            y.float().pow(2).mean().backward()
+
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        return B * SECS * steps / (e0.elapsed_time(e1) / 1e3)
+
+    for sdpa in (False, True):
+        key = "sdpa" if sdpa else "materialised"
+        for B in batch_try:
+            try:
+                out[key] = {"value": one(B, sdpa), "batch": B}
+                break
+            except torch.OutOfMemoryError:
+                gc.collect()
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001
+                out[key] = {"error": repr(e)[:200]}
+                break
+        gc.collect()
+        torch.cuda.empty_cache()
+    vals = [v["value"] for v in out.values() if isinstance(v, dict) and "value" in v]
+    out["value"] = max(vals) if vals else None
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ config 5: mel sweep
+def run_mel_sweep(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from nemo_b200 import _lib as L
+    from nemo_b200.preprocessor import B200MelPreprocessor
+
+    pre = B200MelPreprocessor(sample_rate=SR, window_size=0.025, window_stride=0.01, features=80, n_fft=512, dither=1e-5,
+                              pad_to=0).to(dev).eval()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    peaks = measured_peaks()
+    g = torch.Generator().manual_seed(1234 + rank)
+
+    def point(B, secs, iters):
+        S = int(secs * SR)
+        wav = (torch.rand(B, S, generator=g) * 0.2 - 0.1).to(dev)
+        ln = torch.full((B,), S, dtype=torch.int64, device=dev)
+        for _ in range(3):
+            pre(input_signal=wav, length=ln)
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pre(input_signal=wav, length=ln)
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        ms = ts[len(ts) // 2]
+        T = S // 160 + 1
+        nbytes = B * (4 * S + 4 * 80 * T)  # SURVEY §8(d): 4·S in + 4·80·T_mel out per utterance = 96 kB / audio-s
+        return ms, nbytes
+
+    table = []
+    for secs in SWEEP_SECS:
+        for B in SWEEP_BATCH:
+            ms, nbytes = point(B, secs, 7)
+            table.append({"batch": B, "secs": secs, "ms": round(ms, 4), "audio_s_per_s": B * secs / (ms / 1e3),
+                          "gbs": nbytes / (ms / 1e3) / 1e9, "frac": nbytes / (ms / 1e3) / 1e9 / peaks["hbm"]})
+    # headline point = the batch of config 2 (32 x 30 s), timed like every other config: W warm-up, K steps, one region
+    B, S = 32, int(SECS * SR)
+    wav_host = (torch.rand(B, S, generator=g) * 0.2 - 0.1).pin_memory()
+    len_host = torch.full((B,), S, dtype=torch.int64).pin_memory()
+    wav_dev, len_dev = wav_host.to(dev), len_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, from_host):
+        barrier()
+        n0 = L.lib.b2c_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            if from_host:
+                w, l_ = wav_host.to(dev, non_blocking=True), len_host.to(dev, non_blocking=True)
+                mel, mlen = pre(input_signal=w, length=l_)
+                _ = (mlen.sum() + mel[:, :, 0].sum().long()).item()  # D2H read of the result lengths + a checksum word
+            else:
+                flush.zero_()
+                pre(input_signal=wav_dev, length=len_dev)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), L.lib.b2c_launch_count() - n0
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    n_warm = max(args.warmup, 3)
+    steps = max(args.steps, 20)
+    timed(n_warm, False)
+    # the flush write is inside the loop: time it alone and subtract (it is not part of the path)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(steps):
+        flush.zero_()
+    f1.record()
+    torch.cuda.synchronize()
+    flush_ms = f0.elapsed_time(f1)
+    ms, launches = timed(steps, False)
+    if clocks is not None:
+        clocks.sample()
+    ms = max(ms - flush_ms, 1e-6)
+    ms_e2e, _ = timed(steps, True)
+    if rank == 0:
+        T = S // 160 + 1
+        nbytes = B * (4 * S + 4 * 80 * T)
+        audio_s = world * B * SECS
+        gbs = nbytes / (ms / steps / 1e3) / 1e9
+        out = {
+            "metric": METRICS[5], "value": audio_s * steps / (ms / 1e3), "unit": "audio-sec/s", "n_gpus": world, "steps": steps,
+            "warmup": n_warm, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "AudioToMelSpectrogramPreprocessor (dither-free eval: preemph, STFT 512/400/160, power, 80 mel, "
+                                   "log, per-feature normalise, mask), 32x30 s per GPU; sweep 1-60 s x batch 1-256 in `sweep`",
+                       "global_batch": world * B, "parallelism": f"dp{world}",
+                       "l2": "256 MB flush write between iterations (its own time measured and subtracted)", "sweep": table},
+            "e2e": {"value": audio_s * steps / (ms_e2e / 1e3), "unit": "audio-sec/s",
+                    "h2d_bytes_per_step": world * (wav_host.numel() * 4 + B * 8), "d2h_bytes_per_step": world * 8},
+            "gpu_launches": launches, "clocks": clocks.result(),
+            "roofline": {"bound": "hbm", "kernel": "mel_frames_kernel + mel_normalize_kernel (one pass of the front-end)",
+                         "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                         "traffic": ncu_traffic("mel_frontend_32x30s"), "peak_source": peaks["src"] + " hbm_gbs",
+                         "algorithmic_bytes_per_launch": nbytes},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_baseline(cfg_id=5, steps=2, warmup=1)
+            out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------------------------------ ours
@@ -184,10 +452,21 @@ def run_ours(args):
     from nemo_b200.parallel import FlatGradients
     from nemo_b200.preprocessor import B200MelPreprocessor
 
-    B = args.batch
+    C = CONFIGS[args.config]
+    m = C["model"]
+    if args.batch is not None:
+        B = args.batch
+    elif args.scaling == "strong":
+        gb = C["per_gpu_batch"] * C["ref_gpus"]  # BASELINE's global batch, split over however many GPUs there are
+        if gb % world:
+            raise SystemExit(f"strong scaling: global batch {gb} is not divisible by {world} GPUs")
+        B = gb // world
+    else:
+        B = C["per_gpu_batch"]
     torch.manual_seed(0)  # identical replicas
-    enc = B200ConformerEncoder(feat_in=80, n_layers=LARGE["n_layers"], d_model=LARGE["d_model"], n_heads=LARGE["n_heads"],
-                               conv_kernel_size=LARGE["conv_kernel_size"], subsampling="striding", subsampling_factor=4,
+    enc = B200ConformerEncoder(feat_in=80, n_layers=m["n_layers"], d_model=m["d_model"], n_heads=m["n_heads"],
+                               conv_kernel_size=m["conv_kernel_size"], subsampling=m["subsampling_kind"],
+                               subsampling_factor=m["subsampling_factor"], subsampling_conv_channels=m["subsampling_conv_channels"],
                                dropout=0.1, dropout_pre_encoder=0.1, dropout_emb=0.0, dropout_att=0.1).to(dev).train()
     with torch.no_grad():
         for lyr in enc.layers:
@@ -202,8 +481,8 @@ def run_ours(args):
     wav_host = (torch.rand(B, S, generator=g) * 0.2 - 0.1).pin_memory()
     len_host = torch.full((B,), S, dtype=torch.int64).pin_memory()
     wav_dev, len_dev = wav_host.to(dev), len_host.to(dev)
-    T_enc = ((S // 160 + 1 - 1) // 2 + 1 - 1) // 2 + 1
-    proj = torch.randn(B, LARGE["d_model"], T_enc, device=dev) / (B * T_enc * LARGE["d_model"])
+    T_enc = enc_frames(S, m["subsampling_factor"])
+    proj = torch.randn(B, m["d_model"], T_enc, device=dev) / (B * T_enc * m["d_model"])
     loss_scale = fg.loss_scale()
 
     gemm_events = []
@@ -328,29 +607,37 @@ def run_ours(args):
         value = audio_s * args.steps / (ms / 1e3)
         e2e = audio_s * args.steps / (ms_e2e / 1e3)
         achieved = gf / (gms / 1e3) / 1e12 if gms > 0 else 0.0
-        step_flops = flops_fwd_bwd(B, T_enc)
+        step_flops = model_flops(args.config, B)
         out = {
-            "metric": METRIC, "value": value, "unit": "audio-sec/s", "n_gpus": world, "steps": args.steps,
-            "warmup": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRICS[args.config], "value": value, "unit": "audio-sec/s", "n_gpus": world, "steps": args.steps,
+            "warmup": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"Conformer-CTC-Large 18L d512 h8 k31 striding4x, {B}x30 s per GPU, mel+fwd+bwd+allreduce+AdamW",
+            "config": {"workload": f"{C['name']} {C['tag']}, {B}x30 s per GPU, mel+fwd+bwd+allreduce+AdamW",
                        "global_batch": world * B, "parallelism": f"dp{world}", "dropout": "0.1/0.1/att0.1",
-                       "l2": "inputs+activations per step (>17 GB) exceed the 126 MB L2; no flush needed",
+                       "l2": "inputs+activations per step (GBs) exceed the 126 MB L2; no flush needed",
                        "step_ms": step_ms_value, "host_enqueue_ms": host_ms_value, "step_ms_e2e": step_ms_e2e,
                        "model_tflop_per_step_per_gpu": step_flops / 1e12,
-                       "model_tflops_achieved_per_gpu": step_flops / (ms / args.steps / 1e3) / 1e12},
+                       "model_tflops_achieved_per_gpu": step_flops / (ms / args.steps / 1e3) / 1e12,
+                       "model_flop_utilisation": step_flops / (ms / args.steps / 1e3) / 1e12 / peaks["tflops"]},
             "e2e": {"value": e2e, "unit": "audio-sec/s", "h2d_bytes_per_step": world * (wav_host.numel() * 4 + B * 8),
                     "d2h_bytes_per_step": world * 4},
             "gpu_launches": launches,
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM family, all launches of one step)",
                          "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                         "traffic": None, "peak_source": peaks["src"] + " bf16_tflops_sustained",
-                         "gemm_ms_per_step": gms, "gemm_share_of_step": gms / (ms / args.steps)},
+                         "traffic": ncu_traffic(f"gemm_family_cfg{args.config}"), "peak_source": peaks["src"] + " bf16_tflops_sustained",
+                         "gemm_ms_per_step": gms, "gemm_share_of_step": gms / (ms / args.steps),
+                         "gemm_flop_per_step": gf, "gemm_launches_per_step": len(gemm_events)},
         }
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_baseline(steps=2, warmup=1, batch=1)
+            cb = cpu_baseline(cfg_id=args.config, steps=1 if args.config == 4 else 2, warmup=1, batch=1)
             out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            out["config"]["host"] = cb["host"]
+        if world == 1 and not args.no_eager_baseline:
+            del enc, opt, fg
+            gc.collect()
+            torch.cuda.empty_cache()
+            out["gpu_eager_baseline"] = gpu_eager_baseline(args.config, dev)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -362,11 +649,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="utterances per GPU (default 32 = BASELINE config 2)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5], help="BASELINE.json configs[config-1] (default 2: Conformer-CTC-Large)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the config's per-GPU batch on every GPU; strong: BASELINE's global batch split over the GPUs")
+    ap.add_argument("--batch", type=int, default=None, help="utterances per GPU (overrides the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == 5:
+        run_mel_sweep(args)
     else:
         run_ours(args)
 

@@ -154,13 +154,25 @@ class _Arena:
 
 
 class _WeightCache:
-    """bf16 operand copies of the fp32 master weights in the kernels' layouts, refreshed when a parameter changes
-    (`Tensor._version` bumps on every in-place optimizer update)."""
+    """bf16 operand copies of the fp32 master weights in the kernels' layouts.
+
+    While the module is in training mode the copies are rebuilt on EVERY forward: the weights change every step anyway,
+    and nothing cheap tells us that they did not — `Tensor._version` is not bumped by updates through `p.data`
+    (Novograd / Adafactor / the main-params optimizer wrapper of the reference update that way, novograd.py:141-143).
+    In eval mode the copies are cached, keyed on (data_ptr, _version), and dropped by `invalidate()` — which the module
+    calls from `load_state_dict`, `_apply` (.to / .cuda / .half) and `train()`.  Code that edits weights through `.data`
+    in eval mode must call `B200ConformerEncoder.invalidate_weight_cache()` itself."""
 
     def __init__(self):
         self.store = {}
+        self.always_rebuild = False
+
+    def invalidate(self):
+        self.store.clear()
 
     def get(self, key, params, build):
+        if self.always_rebuild:
+            return build()
         ver = tuple((p.data_ptr(), p._version) for p in params)
         hit = self.store.get(key)
         if hit is None or hit[0] != ver:
@@ -222,6 +234,13 @@ class B200ConformerEncoder(nn.Module):
         if d_model % n_heads or (d_model // n_heads) not in (64, 128): bad.append("head dim must be 64 or 128")
         if conv_kernel_size not in (31, 9, 5): bad.append(f"conv_kernel_size={conv_kernel_size}")
         if d_model % 64: bad.append("d_model % 64")
+        _C = d_model if subsampling_conv_channels == -1 else subsampling_conv_channels
+        _F = feat_in
+        for _ in range(int(math.log2(subsampling_factor)) if subsampling_factor in (4, 8) else 0):
+            _F = (_F - 1) // 2 + 1
+        # conv3x3s2_bwd_weight needs C % 128 == 0 and F2 <= 64; the depthwise / pointwise stages need C % 64 == 0
+        if subsampling == "striding" and (_C % 128 or _F > 64): bad.append(f"striding needs conv_channels % 128 == 0 and feat_in <= 256 (C={_C})")
+        if subsampling == "dw_striding" and _C % 64: bad.append(f"dw_striding needs conv_channels % 64 == 0 (C={_C})")
         if bad:
             raise NotImplementedError("B200ConformerEncoder (hot-path subset, SURVEY.md §8): unsupported " + ", ".join(bad))
         self.d_model, self.n_layers, self._feat_in, self._feat_out = d_model, n_layers, feat_in, d_model
@@ -247,6 +266,25 @@ class B200ConformerEncoder(nn.Module):
         self._wc = _WeightCache()
         self._step = 0
         self._pos_cache = {}
+
+    # ---- weight-operand cache hygiene ---------------------------------------------------------------------------
+    def invalidate_weight_cache(self):
+        """Drop the cached bf16 operand copies (needed only after editing weights through `.data` in eval mode)."""
+        self._wc.invalidate()
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self.__dict__.get("_wc") and self._wc.invalidate()
+        return out
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self._wc.invalidate()
+        return out
+
+    def train(self, mode: bool = True):
+        self.__dict__.get("_wc") and self._wc.invalidate()
+        return super().train(mode)
 
     # ---- reference API surface that callers touch (ctc_models.py / mixins) ------------------------------------
     def set_max_audio_length(self, max_audio_length):
@@ -278,7 +316,9 @@ class B200ConformerEncoder(nn.Module):
             subsampling_factor=pe.subsampling_factor, subsampling_conv_channels=pe._conv_channels,
             ff_expansion_factor=l0.feed_forward1.d_ff // ref.d_model, n_heads=l0.self_attn.h,
             conv_kernel_size=l0.conv.kernel_size, xscaling=ref.xscale is not None, dropout=l0.dropout.p,
-            dropout_pre_encoder=ref.pos_enc.dropout.p, dropout_emb=0.0, dropout_att=l0.self_attn.dropout_rate,
+            dropout_pre_encoder=ref.pos_enc.dropout.p,
+            dropout_emb=(ref.pos_enc.dropout_emb.p if getattr(ref.pos_enc, "dropout_emb", None) is not None else 0.0),
+            dropout_att=l0.self_attn.dropout_rate,
         )
         kw.update(overrides)
         new = cls(**kw)
@@ -298,6 +338,9 @@ class B200ConformerEncoder(nn.Module):
                 f"but got last dimension {audio_signal.shape[-2]}.")
         if not audio_signal.is_cuda:
             raise RuntimeError("B200ConformerEncoder runs on CUDA tensors only (no CPU fallback)")
+        if audio_signal.requires_grad:
+            raise NotImplementedError("gradients w.r.t. the mel input are not produced (the reference front-end runs under "
+                                      "torch.no_grad(), audio_preprocessing.py:94)")
         if length is None:
             length = audio_signal.new_full((audio_signal.size(0),), audio_signal.size(-1), dtype=torch.int64)
         params = [p for _, p in self.named_parameters()]
@@ -311,6 +354,7 @@ class B200ConformerEncoder(nn.Module):
     # bf16 operand preparation ------------------------------------------------------------------------------------
     def _weights(self):
         wc, pe = self._wc, self.pre_encode
+        wc.always_rebuild = self.training
         C, F2, d = pe._conv_channels, pe._f_out, self.d_model
         W = {}
         w1 = pe.conv[0].weight  # [C,1,3,3] → [C,16] bf16: the 9 taps, then zeros (column 9 multiplies the patch's ones)
@@ -446,6 +490,7 @@ class _EncoderFn(torch.autograd.Function):
 
         # ---- conformer layers ---------------------------------------------------------------------------------
         layers_saved = []
+        taps = enc.__dict__.get("_debug_taps")
         for li, lyr in enumerate(enc.layers):
             sv = {}
             site = li * 16
@@ -514,6 +559,8 @@ class _EncoderFn(torch.autograd.Function):
             sv["out"] = (xd, m5, r5)
             layers_saved.append(sv)
             x = xo
+            if taps is not None:  # debugging / depth-resolved parity tests: per-layer outputs [B,T,d] fp32
+                taps.append(xo.view(B, T, d).clone())
 
         ctx.enc, ctx.S, ctx.layers_saved, ctx.W, ctx.arena = enc, S, layers_saved, W, arena
         ctx.meta = dict(B=B, T=T, M=M, Ts=Ts, Fs=Fs, seed=seed, p_drop=p_drop, p_pre=p_pre, p_att=p_att, training=training,
@@ -548,8 +595,14 @@ class _EncoderFn(torch.autograd.Function):
         fg = enc.__dict__.get("_flat_grads")
         G = {}
         if fg is not None:
+            fg.bind()
             for n, p in zip(names, plist):
-                G[n] = fg.view(n).view_as(p) if n in fg.offsets else torch.zeros_like(p)
+                if n in fg.offsets:
+                    G[n] = fg.view(n).view_as(p)
+                elif p.requires_grad:
+                    raise RuntimeError(f"FlatGradients was built while '{n}' was frozen; rebuild it after unfreezing")
+                else:
+                    G[n] = torch.zeros_like(p)  # frozen parameter: scratch, never read
         else:
             sizes = [p.numel() for p in plist]
             flat = torch.zeros(sum(sizes), dtype=F32, device=dev)
@@ -561,6 +614,8 @@ class _EncoderFn(torch.autograd.Function):
         arena = _Arena(dev)
         _empty = arena.alloc  # noqa: F811
         dr = dout.transpose(1, 2).contiguous().view(M, d).to(F32)
+        if dr.data_ptr() == dout.data_ptr():  # fp32 [B,T,d]-contiguous grad_output: never mutate autograd's tensor
+            dr = dr.clone()
         t16 = _empty(M, d, dev=dev)
 
         def ln_bwd(dy, dy_bf16, xin, norm_name, norm, mean, rstd, accumulate, nxt, nscale, site, p):
@@ -651,7 +706,7 @@ class _EncoderFn(torch.autograd.Function):
             ffn_bwd("feed_forward1", lyr.feed_forward1, "norm_feed_forward1", lyr.norm_feed_forward1, S_FF1_HID, None, 1.0,
                     0, 0.0)
             if fg is not None:
-                fg.ready(*fg.span(pfx))
+                fg.ready_prefix(pfx)
 
         # ---- pre_encode: xscale + dropout backward, out Linear, convolutions
         L.call("scale_drop_cast", dr, t16, M * d, enc.xscale or 1.0, p_pre, seed, enc.n_layers * 16)
@@ -701,7 +756,7 @@ class _EncoderFn(torch.autograd.Function):
         # the activations are dead now: drop them even if the caller keeps the loss (and with it this node) alive
         ctx.S = ctx.layers_saved = ctx.arena = None
         if fg is not None:
-            fg.ready(*fg.span("pre_encode."))
+            fg.ready_prefix("pre_encode.")
             return (None,) * (3 + len(plist))
         grads = [G[n] if p.requires_grad else None for n, p in zip(names, plist)]
         return (None, None, None, *grads)

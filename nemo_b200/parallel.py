@@ -23,9 +23,10 @@ import torch.distributed as dist
 class FlatGradients:
     """Owns the flat gradient buffer of a module and the layer-wise overlapped all-reduce."""
 
-    def __init__(self, module: torch.nn.Module, process_group=None, grad_dtype=torch.float32):
+    def __init__(self, module: torch.nn.Module, process_group=None, grad_dtype=torch.float32, defer: bool = False):
         self.module = module
         self.group = process_group
+        self.defer = defer
         params = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
         self.names = [n for n, _ in params]
         self.sizes = [p.numel() for _, p in params]
@@ -38,8 +39,26 @@ class FlatGradients:
             p.grad = self.flat[off:off + sz].view_as(p)
             off += sz
         self._handles: List = []
-        self._reduced_upto: Optional[int] = None
+        self._reduced = False  # an all-reduce has been launched on this buffer since the last zero()
+        self._params = dict(params)
         module.__dict__["_flat_grads"] = self  # encoder backward writes here and calls `ready(lo, hi)`
+
+    def bind(self):
+        """Called at the start of every backward: (re-)attach `p.grad` to the flat views — `optimizer.zero_grad()` with
+        the default set_to_none=True (what Lightning / NeMo call) detaches them — and refuse a second backward into a
+        buffer that has already been all-reduced (that would reduce the first micro-batch twice).  Use `zero()` instead
+        of `zero_grad()`; for gradient accumulation construct with `defer=True` (one all-reduce in `finish()`)."""
+        if self._reduced and self._world() > 1:
+            raise RuntimeError("FlatGradients: backward into an already all-reduced buffer; call zero() between steps "
+                               "(gradient accumulation: FlatGradients(..., defer=True))")
+        for n, p in self._params.items():
+            lo, hi = self.offsets[n]
+            g = p.grad
+            if g is None or g.data_ptr() != self.flat.data_ptr() + lo * self.flat.element_size():
+                view = self.flat[lo:hi].view_as(p)
+                if g is not None:
+                    view.add_(g.to(view.dtype))  # keep what the caller accumulated outside the buffer
+                p.grad = view
 
     # ---- called by the backward orchestration ------------------------------------------------------------------
     def view(self, name: str) -> torch.Tensor:
@@ -51,9 +70,18 @@ class FlatGradients:
         his = [v[1] for k, v in self.offsets.items() if k.startswith(prefix)]
         return (min(los), max(his)) if los else None
 
+    def ready_prefix(self, prefix: str):
+        """All gradients of the parameters under `prefix` are final (a fully frozen sub-module has no span: no-op)."""
+        sp = self.span(prefix)
+        if sp is not None:
+            self.ready(*sp)
+
     def ready(self, lo: int, hi: int):
         """Gradients in flat[lo:hi] are final (their kernels are enqueued on the current stream)."""
+        if self.defer:
+            return
         if self._world() > 1 and hi > lo:
+            self._reduced = True
             self._handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     # ---- called by the training loop ---------------------------------------------------------------------------
@@ -62,9 +90,13 @@ class FlatGradients:
 
     def zero(self):
         self.flat.zero_()
+        self._reduced = False
 
     def finish(self):
         """Wait for the outstanding all-reduces (the current stream waits; no host sync for NCCL)."""
+        if self.defer and self._world() > 1:
+            self._reduced = True
+            self._handles.append(dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
         for h in self._handles:
             h.wait()
         self._handles.clear()

@@ -216,8 +216,9 @@ def rel_shift(x: torch.Tensor) -> torch.Tensor:
     return x
 
 
-def rel_pos_mha(sd, p: str, x: torch.Tensor, pos_emb: torch.Tensor, att_mask: torch.Tensor, n_heads: int):
-    """RelPositionMultiHeadAttention.forward (non-SDPA branch) — multi_head_attention.py:272-354,125-146.
+def rel_pos_mha(sd, p: str, x: torch.Tensor, pos_emb: torch.Tensor, att_mask: torch.Tensor, n_heads: int, use_sdpa: bool = False):
+    """RelPositionMultiHeadAttention.forward — multi_head_attention.py:272-354,125-146: the default materialised branch
+    (:344-349) and, with use_sdpa, the `use_pytorch_sdpa` branch (:316-343: matrix_bd as a float attn_mask).
     Dropout is not restated (all parity runs use p=0 / eval)."""
     B, T, d = x.shape
     dk = d // n_heads
@@ -229,6 +230,12 @@ def rel_pos_mha(sd, p: str, x: torch.Tensor, pos_emb: torch.Tensor, att_mask: to
     q_u = (q + sd[f"{p}pos_bias_u"]).transpose(1, 2)
     q_v = (q + sd[f"{p}pos_bias_v"]).transpose(1, 2)
     bd = rel_shift(torch.matmul(q_v, pe.transpose(-2, -1)))
+    if use_sdpa:
+        m = att_mask.unsqueeze(1)
+        bd = (bd[:, :, :, :T] * (1.0 / math.sqrt(dk))).masked_fill(m, -INF_VAL)
+        out = F.scaled_dot_product_attention(q_u, k, v, attn_mask=bd, dropout_p=0.0)
+        out = out.masked_fill(torch.all(m, dim=-1).unsqueeze(-1).expand(-1, out.size(1), -1, out.size(-1)), 0.0)
+        return lin("linear_out", out.transpose(1, 2).reshape(B, T, d))
     ac = torch.matmul(q_u, k.transpose(-2, -1))
     scores = (ac + bd[:, :, :, :T]) / math.sqrt(dk)
     m = att_mask.unsqueeze(1)
@@ -275,10 +282,10 @@ def _ln(sd, p, x):
     return F.layer_norm(x, (x.shape[-1],), sd[f"{p}.weight"], sd[f"{p}.bias"], 1e-5)
 
 
-def conformer_layer(sd, p: str, x, pos_emb, att_mask, pad_mask, n_heads: int, training: bool, bn_out=None):
+def conformer_layer(sd, p: str, x, pos_emb, att_mask, pad_mask, n_heads: int, training: bool, bn_out=None, use_sdpa=False):
     """ConformerLayer.forward — conformer_modules.py:160-233 (dropout omitted: parity runs use p=0)."""
     r = x + 0.5 * feed_forward(sd, f"{p}feed_forward1.", _ln(sd, f"{p}norm_feed_forward1", x))
-    r = r + rel_pos_mha(sd, f"{p}self_attn.", _ln(sd, f"{p}norm_self_att", r), pos_emb, att_mask, n_heads)
+    r = r + rel_pos_mha(sd, f"{p}self_attn.", _ln(sd, f"{p}norm_self_att", r), pos_emb, att_mask, n_heads, use_sdpa)
     r = r + conv_module(sd, f"{p}conv.", _ln(sd, f"{p}norm_conv", r), pad_mask, training, bn_out)
     r = r + 0.5 * feed_forward(sd, f"{p}feed_forward2.", _ln(sd, f"{p}norm_feed_forward2", r))
     return _ln(sd, f"{p}norm_out", r)
@@ -298,6 +305,7 @@ def encoder_forward(
     training: bool = False,
     bn_out: Optional[dict] = None,
     return_layers: bool = False,
+    use_sdpa: bool = False,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """ConformerEncoder.forward_internal — conformer_encoder.py:593-759, full-context offline path.
     audio_signal [B,feat_in,T_mel], length [B] → (outputs [B,d_model,T'], encoded_lengths [B] i64)."""
@@ -314,7 +322,7 @@ def encoder_forward(
     pad_mask = ~valid
     taps = []
     for i in range(n_layers):
-        x = conformer_layer(sd, f"layers.{i}.", x, pos_emb, att_mask, pad_mask, n_heads, training, bn_out)
+        x = conformer_layer(sd, f"layers.{i}.", x, pos_emb, att_mask, pad_mask, n_heads, training, bn_out, use_sdpa)
         if return_layers:
             taps.append(x)
     out = x.transpose(1, 2)

@@ -1,0 +1,144 @@
+"""Full-depth parity at the BASELINE.json configurations: the complete 18 / 17 / 24-layer encoders of
+configs[1..3] at 30 s utterances, forward + backward, against the fp32 oracle AND the oracle under torch.autocast(bf16)
+(= what the reference itself computes with `trainer.precision=bf16`), error printed per depth.
+
+Gates (speed mode = bf16 operands): err(cuda, oracle_fp32) <= 1.5 * err(autocast_oracle, oracle_fp32) + 2e-3
+for the output and every layer tap; gradients <= 2 * autocast error + 2e-2.  Lengths bit-exact."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from nemo_b200.encoder import B200ConformerEncoder
+    from nemo_b200.preprocessor import B200MelPreprocessor
+    from oracle import conformer_oracle as O
+    DEV = torch.device("cuda:0")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def rel_l2(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12)).item()
+
+
+FULL = {
+    # name: (model cfg, batch, ragged)
+    "cfg2_conformer_ctc_large_18L": (dict(n_layers=18, d_model=512, n_heads=8, conv_kernel_size=31, subsampling_kind="striding",
+                                          subsampling_factor=4, subsampling_conv_channels=512), 2),
+    "cfg3_fastconformer_large_17L": (dict(n_layers=17, d_model=512, n_heads=8, conv_kernel_size=9, subsampling_kind="dw_striding",
+                                          subsampling_factor=8, subsampling_conv_channels=256), 2),
+    "cfg4_conformer_transducer_xl_24L": (dict(n_layers=24, d_model=1024, n_heads=8, conv_kernel_size=5, subsampling_kind="striding",
+                                              subsampling_factor=4, subsampling_conv_channels=1024), 1),
+}
+
+
+def _oracle(sd, mel, mlen, cfg, autocast, r=None, taps=False):
+    params = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and "running" not in k) else v) for k, v in sd.items()}
+    kw = dict(n_layers=cfg["n_layers"], d_model=cfg["d_model"], n_heads=cfg["n_heads"], subsampling_kind=cfg["subsampling_kind"],
+              subsampling_factor=cfg["subsampling_factor"], training=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        res = O.encoder_forward(params, mel, mlen, return_layers=taps, **kw)
+    y, ylen = res[0], res[1]
+    grads = None
+    if r is not None:
+        ((y.float() * r).sum() / y.shape[0]).backward()
+        grads = {k: p.grad for k, p in params.items() if isinstance(p, torch.Tensor) and p.requires_grad and p.grad is not None}
+    return y.detach().float(), ylen, grads, ([t.detach().float() for t in res[2]] if taps else None)
+
+
+@pytest.mark.parametrize("name", list(FULL))
+def test_full_depth_forward_backward(name):
+    cfg, B = FULL[name]
+    sd = O.init_state_dict(seed=11, **cfg)
+    enc = B200ConformerEncoder(feat_in=80, n_layers=cfg["n_layers"], d_model=cfg["d_model"], n_heads=cfg["n_heads"],
+                               conv_kernel_size=cfg["conv_kernel_size"], subsampling=cfg["subsampling_kind"],
+                               subsampling_factor=cfg["subsampling_factor"], subsampling_conv_channels=cfg["subsampling_conv_channels"],
+                               dropout=0.0, dropout_pre_encoder=0.0, dropout_emb=0.0, dropout_att=0.0)
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.to(DEV).train()
+    sd = {k: v.to(DEV) for k, v in sd.items()}
+    pre = B200MelPreprocessor(window_size=0.025, window_stride=0.01, features=80, n_fft=512, pad_to=0).to(DEV).eval()
+    wav, wlen = O.synthetic_waveforms(B, 30.0, ragged=True)
+    if B > 1:
+        wlen[-1] = 30 * 16000 - 160 * 411  # a clearly shorter utterance: masks matter in every layer
+    mel, mlen = pre(input_signal=wav.to(DEV), length=wlen.to(DEV))
+    g = torch.Generator().manual_seed(3)
+    enc.__dict__["_debug_taps"] = taps = []
+    y, ylen = enc(audio_signal=mel, length=mlen)
+    enc.__dict__["_debug_taps"] = None
+    r = torch.randn(y.shape, generator=g).to(DEV)
+    ((y.float() * r).sum() / y.shape[0]).backward()
+    y_ref, ylen_ref, g_ref, t_ref = _oracle(sd, mel, mlen, cfg, False, r, taps=True)
+    y_ac, _, g_ac, t_ac = _oracle(sd, mel, mlen, cfg, True, r, taps=True)
+    assert torch.equal(ylen, ylen_ref)
+    for i in (0, 1, 3, 7, 11, 15, cfg["n_layers"] - 1):
+        if i < cfg["n_layers"]:
+            print(f"[{name}] depth {i + 1:2d}: rel-L2 vs fp32 oracle  cuda {rel_l2(taps[i], t_ref[i]):.3e} | autocast-oracle {rel_l2(t_ac[i], t_ref[i]):.3e}")
+    for i in range(cfg["n_layers"]):
+        assert rel_l2(taps[i], t_ref[i]) <= 1.5 * rel_l2(t_ac[i], t_ref[i]) + 2e-3, f"layer {i}"
+    e, e_ac = rel_l2(y, y_ref), rel_l2(y_ac, y_ref)
+    mx = ((y.float() - y_ref).abs().max() / y_ref.abs().max()).item()
+    print(f"[{name}] output rel-L2 cuda {e:.3e} | autocast-oracle {e_ac:.3e}; max-abs/max|y| cuda {mx:.3e}")
+    assert e <= 1.5 * e_ac + 2e-3
+    bad = []
+    worst = (0.0, "")
+    for k, p in enc.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        gr = g_ref[k]
+        if gr.norm() <= 1e-6 * gr.numel() ** 0.5:
+            continue
+        eg, eg_ac = rel_l2(p.grad, gr), rel_l2(g_ac[k], gr)
+        if eg > worst[0]:
+            worst = (eg, k)
+        if eg > 2.0 * eg_ac + 2e-2:
+            bad.append((k, eg, eg_ac))
+    print(f"[{name}] worst parameter-gradient rel-L2 {worst[0]:.3e} ({worst[1]})")
+    for k, eg, eg_ac in bad:
+        print(f"[{name}] GRAD FAIL {k}: cuda {eg:.3e} autocast-oracle {eg_ac:.3e}")
+    assert not bad
+
+
+def test_dither_is_gaussian_seeded_and_train_only():
+    """a4: dither (features.py:435-436, training only): x += dither * randn.  The kernel draws its own Philox / Box-Muller
+    normals, so the check is statistical: with pre-emphasis off and a zero waveform the STFT input is pure dither."""
+    from nemo_b200 import _lib as L
+
+    B, S = 4, 16000 * 4
+    pre = B200MelPreprocessor(window_size=0.025, window_stride=0.01, features=80, n_fft=512, dither=1e-5, pad_to=0).to(DEV)
+    x = (torch.rand(B, S, generator=torch.Generator().manual_seed(0)) * 0.2 - 0.1).to(DEV)
+    ln = torch.full((B,), S, dtype=torch.int64, device=DEV)
+    pre.eval()
+    e1, _ = pre(input_signal=x, length=ln)
+    e2, _ = pre(input_signal=x, length=ln)
+    assert torch.equal(e1, e2)  # eval: no dither, deterministic
+    pre.train()
+    t1, _ = pre.featurizer.forward_raw(x, ln)
+    t2, _ = pre.featurizer.forward_raw(x, ln)
+    pre.eval()
+    e_raw, _ = pre.featurizer.forward_raw(x, ln)
+    assert not torch.equal(t1, t2)            # a new draw every call
+    assert not torch.equal(t1, e_raw)         # train != eval
+    # dither 1e-5 on a 0.1-amplitude signal moves log-mel by ~1e-4 relative: tiny but non-zero, and never large
+    assert (t1 - e_raw).abs().max().item() < 5e-2
+    # same seed => same output (the module's seed counter is the Philox key)
+    pre.train()
+    pre.featurizer._seed = 41
+    a, _ = pre.featurizer.forward_raw(x, ln)
+    pre.featurizer._seed = 41
+    b, _ = pre.featurizer.forward_raw(x, ln)
+    assert torch.equal(a, b)
+    # distribution: silence + dither sigma → power spectrum of white noise.  E[|X_k|^2] = sigma^2 * sum(w^2) for every bin, so
+    # mel[m] = sigma^2 * sum(w^2) * sum_k fb[m,k]; compare the time-averaged linear mel energies with that expectation.
+    sig = 1e-2
+    pre2 = B200MelPreprocessor(window_size=0.025, window_stride=0.01, features=80, n_fft=512, dither=sig, pad_to=0, preemph=0.0).to(DEV).train()
+    z = torch.zeros(2, 16000 * 20, device=DEV)
+    zl = torch.full((2,), z.shape[1], dtype=torch.int64, device=DEV)
+    raw, rl = pre2.featurizer.forward_raw(z, zl)
+    lin = (raw[:, :, 2:-3].exp() - 2 ** -24).mean(dim=(0, 2))  # interior frames only (no edge padding)
+    w = pre2.featurizer.window.double()
+    expect = (sig ** 2) * (w ** 2).sum() * pre2.featurizer.fb[0].double().sum(dim=1)
+    ratio = (lin.double() / expect).cpu()
+    print("dither: mel-energy / expectation: min %.3f max %.3f mean %.4f" % (ratio.min(), ratio.max(), ratio.mean()))
+    assert (ratio - 1).abs().max().item() < 0.05  # ~4000 frames x several bins per filter: < 5 % sampling error
+    assert abs(ratio.mean().item() - 1) < 0.01

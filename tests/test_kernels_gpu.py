@@ -378,7 +378,7 @@ def test_relpos_attention_dropout_statistics():
 
 
 # ------------------------------------------------------------------------------------------------------- subsampling
-@pytest.mark.parametrize("B,F,T,C", [(2, 80, 131, 128), (3, 80, 301, 256), (2, 80, 64, 512)])
+@pytest.mark.parametrize("B,F,T,C", [(2, 80, 131, 128), (3, 80, 301, 256), (2, 80, 64, 512), (2, 80, 203, 1024)])
 def test_subsampling_convs(B, F, T, C):
     Fn = torch.nn.functional
     lengths = torch.tensor([T, max(T - 37, 3), 9][:B], dtype=torch.int64, device=DEV)
