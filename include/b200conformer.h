@@ -118,10 +118,12 @@ int b2c_log_softmax_bwd(const float* dlogp, const float* logp, void* dlogits_bf1
 int b2c_dwconv_fwd(const void* u_bf16, const float* w, const float* bias, void* c_bf16, float* bn_sum, float* bn_sumsq,
                    int B, int T, int d, int k, void* stream);
 /* BatchNorm1d finalise: train → batch mean/var (biased) into scale/shift and momentum update of running stats
- * (unbiased var); eval → running stats.  scale = gamma*rstd, shift = beta - mean*scale. */
+ * (unbiased var), `num_batches_tracked` (int64 device word, may be NULL) += 1; eval → running stats.
+ * scale = gamma*rstd, shift = beta - mean*scale. */
 int b2c_bn_finalize(const float* bn_sum, const float* bn_sumsq, const float* gamma, const float* beta,
                     float* running_mean, float* running_var, float* scale, float* shift, float* mean_out,
-                    float* rstd_out, long long count, int d, int training, float momentum, float eps, void* stream);
+                    float* rstd_out, long long count, int d, int training, float momentum, float eps,
+                    long long* num_batches_tracked, void* stream);
 /* s = bf16(silu(bf16(c*scale+shift))) */
 int b2c_bn_silu_fwd(const void* c_bf16, const float* scale, const float* shift, void* s_bf16, long long M, int d,
                     void* stream);
@@ -205,6 +207,49 @@ int b2c_relpos_table(void* pos_bf16, float* pos_f32, int T, int d, void* stream)
  * len_in32 [B] = int32 copy of the input, len_stage [n_convs*B] int32 per stage, len_out64 [B]. */
 int b2c_subsample_lengths(const int64_t* len_in, int32_t* len_in32, int32_t* len_stage, int64_t* len_out64, int B,
                           int n_convs, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ training-step runtime
+ * Device-side RNG counter: every dropout / dither key becomes `seed + *counter * golden-ratio`, so a CUDA-graph replay of a
+ * captured step (whose by-value seeds are frozen) still draws fresh masks each step.  b2c_set_seed_counter registers the
+ * device word (NULL = by-value seeds only, the default); b2c_counter_add advances it (first node of a captured step). */
+int b2c_set_seed_counter(const unsigned long long* counter);
+int b2c_counter_add(unsigned long long* counter, unsigned long long inc, void* stream);
+
+/* Multi-tensor tables (device arrays).  `blocks` is an int32 [n_blocks, 2] map block -> (tensor index, 2048-element chunk). */
+typedef struct {
+  void* ptr;          /* fp32 parameter tensor (contiguous) */
+  long long offset;   /* its offset (elements) in the flat gradient / moment buffers */
+  long long numel;
+  int flags;          /* bit 0: no weight decay for this tensor */
+  int reserved;
+} b2c_tensor_entry;
+
+typedef struct {
+  float lr, beta1, beta2, eps, weight_decay;
+  int noam_d_model;   /* > 0: NoamAnnealing (lr_scheduler.py:518-575): lr * d_model^-0.5 * min(s^-0.5, s * warmup^-1.5) */
+  int noam_warmup;
+  float noam_min_lr;
+} b2c_adamw_hyper;
+
+/* One optimizer step over all tensors of `table`: AdamW with decoupled weight decay (torch.optim.AdamW arithmetic =
+ * NeMo's `optim.name: adamw`, nemo/core/classes/modelPT.py:650-823; conformer_ctc_bpe.yaml:175-192) reading the flat fp32
+ * gradient buffer (scaled by grad_scale), exp_avg / exp_avg_sq flat fp32 moments.  `state` [1] f64 = step count (device,
+ * incremented here), `scalars` [4] f32 scratch.  The learning rate is evaluated on the device: capturable in a CUDA graph. */
+int b2c_adamw_step(const b2c_tensor_entry* table, const int32_t* blocks, int n_blocks, const float* grad_flat, float* exp_avg,
+                   float* exp_avg_sq, double* state, float* scalars, const b2c_adamw_hyper* hyper, float grad_scale,
+                   void* stream);
+
+typedef struct {
+  const void* src;    /* fp32 [A, B, C] contiguous */
+  void* dst;          /* bf16 (or fp32 if flags & 2): element (a, b, c) is written at a*sa + b*sb + c*sc */
+  int A, B, C;
+  int flags;
+  long long sa, sb, sc;
+} b2c_prep_entry;
+
+/* fp32 master weights -> operand copies in kernel layouts (casts, GLU interleave, conv taps-major, flatten order), one
+ * launch for the whole encoder; replaces per-tensor b2c_cast_bf16 / b2c_permute3_* calls of the forward. */
+int b2c_prep_weights(const b2c_prep_entry* table, const int32_t* blocks, int n_blocks, void* stream);
 
 #ifdef __cplusplus
 }

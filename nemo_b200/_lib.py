@@ -27,6 +27,36 @@ class Epilogue(C.Structure):
     ]
 
 
+class TensorEntry(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("offset", C.c_longlong), ("numel", C.c_longlong), ("flags", C.c_int), ("reserved", C.c_int)]
+
+
+class PrepEntry(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("A", C.c_int), ("B", C.c_int), ("C", C.c_int), ("flags", C.c_int),
+                ("sa", C.c_longlong), ("sb", C.c_longlong), ("sc", C.c_longlong)]
+
+
+class AdamWHyper(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+                ("noam_d_model", C.c_int), ("noam_warmup", C.c_int), ("noam_min_lr", C.c_float)]
+
+
+CHUNK = 2048  # elements per block of the multi-tensor kernels (csrc/optim.cu)
+
+
+def upload_table(entries, numels, device):
+    """(table, blocks, n_blocks): a ctypes struct array and its block -> (tensor, chunk) map as device tensors."""
+    import torch
+
+    arr = (type(entries[0]) * len(entries))(*entries)
+    raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+    blocks = []
+    for i, n in enumerate(numels):
+        blocks += [(i, c) for c in range((int(n) + CHUNK - 1) // CHUNK)]
+    bl = torch.tensor(blocks, dtype=torch.int32).to(device)
+    return raw, bl, len(blocks)
+
+
 EPI_BF16, EPI_SILU, EPI_RESID_F32, EPI_GLU_MASK, EPI_DSILU, EPI_RELU_MASK, EPI_ACCUM_F32, EPI_RELU_BWD = range(8)
 
 if not os.path.exists(LIB_PATH):
@@ -38,7 +68,7 @@ lib = C.CDLL(LIB_PATH)
 
 _CTYPE = {
     "int": C.c_int, "float": C.c_float, "long long": C.c_longlong, "unsigned long long": C.c_ulonglong,
-    "unsigned int": C.c_uint, "size_t": C.c_size_t, "int64_t": C.c_int64, "int32_t": C.c_int32,
+    "unsigned int": C.c_uint, "size_t": C.c_size_t, "int64_t": C.c_int64, "int32_t": C.c_int32, "double": C.c_double,
 }
 
 

@@ -14,6 +14,9 @@
 
 namespace b2c {
 
+B2C_DEFINE_SEED_SETTER(set_seed_counter_attn)
+
+
 constexpr int BQ = 64;    // query rows per CTA (4 warps x 16)
 constexpr int BKV = 64;   // keys per inner tile
 constexpr int BAND = 80;  // 16 + 64 - 1 rounded up to a multiple of 16

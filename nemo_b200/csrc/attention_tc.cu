@@ -18,6 +18,9 @@
 
 namespace b2c {
 
+B2C_DEFINE_SEED_SETTER(set_seed_counter_attn_tc)
+
+
 namespace atc {
 constexpr int BQ = 128, BKV = 64, DK = 64, BAND = 192;
 constexpr int kStages = 3;

@@ -328,6 +328,22 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---- device-side seed counter (CUDA-graph replay): every stateless RNG key is `seed + counter * golden`, where `seed` is the
+// by-value kernel argument (frozen inside a captured graph) and `counter` lives in device memory, advanced once per step by
+// b2c_counter_add — so a replayed graph draws fresh dropout / dither masks each step while forward and backward of the SAME
+// step still agree.  One __constant__ pointer per translation unit (no relocatable device code), set by
+// b2c_set_seed_counter through the per-TU setters below; nullptr (the default) = by-value seed only.
+static __constant__ const unsigned long long* c_seed_ctr = nullptr;
+__device__ __forceinline__ unsigned long long seed_eff(unsigned long long seed) {
+  const unsigned long long* p = c_seed_ctr;
+  return p ? seed + __ldg(p) * 0x9E3779B97F4A7C15ull : seed;
+}
+#define B2C_DEFINE_SEED_SETTER(name)                                                        \
+  int name(const unsigned long long* p) {                                                   \
+    B2C_CUDA(cudaMemcpyToSymbol(c_seed_ctr, &p, sizeof(p), 0, cudaMemcpyHostToDevice));     \
+    return B2C_OK;                                                                          \
+  }
+
 // ---- Philox-4x32-10 counter RNG (mel dither; the dropout masks use the cheaper chunked hash below)
 __device__ __forceinline__ uint4 philox4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
@@ -350,6 +366,7 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
 // Hot loops that walk aligned chunks pay ~3 integer ops per pair; `dropout_hash(pair_idx)` is the same function for
 // arbitrary indices.
 __device__ __forceinline__ uint32_t dropout_base(uint64_t seed, uint32_t site, uint64_t chunk_idx) {
+  seed = seed_eff(seed);
   return hash32((uint32_t)chunk_idx ^ (uint32_t)seed ^ ((uint32_t)(chunk_idx >> 32) * 0x9E3779B1U) ^ (site * 0x85EBCA77U) ^
                 __funnelshift_l((uint32_t)(seed >> 32), (uint32_t)(seed >> 32), 13));
 }

@@ -89,8 +89,9 @@ __global__ void bn_finalize_kernel(const float* __restrict__ bn_sum, const float
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ rstd_out, float count, int d, int training, float momentum,
-                                   float eps) {
+                                   float eps, long long* __restrict__ num_batches_tracked) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && num_batches_tracked) *num_batches_tracked += 1;  // nn.BatchNorm1d bookkeeping
   if (c >= d) return;
   float mean, var;
   if (training) {
@@ -453,10 +454,11 @@ extern "C" int b2c_dwconv_fwd(const void* u_bf16, const float* w, const float* b
 extern "C" int b2c_bn_finalize(const float* bn_sum, const float* bn_sumsq, const float* gamma, const float* beta,
                                float* running_mean, float* running_var, float* scale, float* shift, float* mean_out,
                                float* rstd_out, long long count, int d, int training, float momentum, float eps,
-                               void* stream) {
+                               long long* num_batches_tracked, void* stream) {
   bn_finalize_kernel<<<(d + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bn_sum, bn_sumsq, gamma, beta, running_mean,
                                                                        running_var, scale, shift, mean_out, rstd_out,
-                                                                       (float)count, d, training, momentum, eps);
+                                                                       (float)count, d, training, momentum, eps,
+                                                                       num_batches_tracked);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
 }

@@ -6,6 +6,9 @@
 
 namespace b2c {
 
+B2C_DEFINE_SEED_SETTER(set_seed_counter_elementwise)
+
+
 constexpr int kMaxVecLimit = 8;  // d <= 1024 (8 float4 per lane)
 
 template <int kMaxVec>

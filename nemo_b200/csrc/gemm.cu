@@ -22,6 +22,9 @@
 
 namespace b2c {
 
+B2C_DEFINE_SEED_SETTER(set_seed_counter_gemm)
+
+
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kEpiWarps = 16;
@@ -761,8 +764,18 @@ static int dispatch_mode(const void* A, const void* B, int lda, int ldb, int a_m
     B2C_LAUNCH_CHECK();
     return B2C_OK;
   }
-  // tile width: 256 when it divides the work well, else 128
-  const int BN = (p.N >= 256 && p.N % 256 == 0) ? 256 : 128;
+  // tile width: 256 when it divides the work well, else 128.  Small-M launches (2 utterances per GPU: 12 row tiles) leave
+  // most CTA pairs idle with 256-wide tiles: take the width whose (rounds of CTA pairs) x (cost per tile) is smaller —
+  // a 128-wide tile costs ~0.55 of a 256-wide one (half the MMAs, less operand reuse).  Split-K (fp32 accumulate) launches
+  // fill the machine through their split factor instead.
+  int BN = (p.N >= 256 && p.N % 256 == 0) ? 256 : 128;
+  if (BN == 256 && MODE != B2C_EPI_ACCUM_F32) {
+    const int clusters = num_sms() / kCluster;
+    const long long t256 = (long long)((((p.M + BM - 1) / BM) + kCluster - 1) / kCluster) * (p.N / 256);
+    const double c256 = (double)((t256 + clusters - 1) / clusters);
+    const double c128 = 0.55 * (double)((2 * t256 + clusters - 1) / clusters);
+    if (c128 < c256) BN = 128;
+  }
   const int kb_total = (p.K + BK - 1) / BK;
   if (MODE == B2C_EPI_ACCUM_F32) {
     // split-K so that the (pair-tile x split) work units fill whole waves of CTA pairs: minimise

@@ -13,6 +13,9 @@
 
 namespace b2c {
 
+B2C_DEFINE_SEED_SETTER(set_seed_counter_mel)
+
+
 constexpr int kNfft = 512;
 constexpr int kFramesPerCta = 64;
 constexpr int kMelWarps = 8;
@@ -115,6 +118,7 @@ mel_frames_kernel(const float* __restrict__ x, const int64_t* __restrict__ lengt
 
   // y[n] for n in [n0, n0+ylen): pre-emphasised, masked, (dithered) signal; n0 = t0*hop - n_fft/2 + woff
   const int64_t len = length[b];
+  if (dither > 0.f) seed = seed_eff(seed);
   const int64_t n0 = (int64_t)t0 * hop - kNfft / 2 + woff;
   const float* xb = x + (size_t)b * S;
   for (int i = threadIdx.x; i < ylen; i += blockDim.x) {

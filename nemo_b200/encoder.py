@@ -154,31 +154,20 @@ class _Arena:
 
 
 class _WeightCache:
-    """bf16 operand copies of the fp32 master weights in the kernels' layouts.
+    """Validity flag of the bf16 operand copies of the fp32 master weights (kernel layouts, `_operand_plan`).
 
-    While the module is in training mode the copies are rebuilt on EVERY forward: the weights change every step anyway,
+    While the module is in training mode the copies are refilled on EVERY forward: the weights change every step anyway,
     and nothing cheap tells us that they did not — `Tensor._version` is not bumped by updates through `p.data`
     (Novograd / Adafactor / the main-params optimizer wrapper of the reference update that way, novograd.py:141-143).
-    In eval mode the copies are cached, keyed on (data_ptr, _version), and dropped by `invalidate()` — which the module
-    calls from `load_state_dict`, `_apply` (.to / .cuda / .half) and `train()`.  Code that edits weights through `.data`
-    in eval mode must call `B200ConformerEncoder.invalidate_weight_cache()` itself."""
+    In eval mode the copies are reused while every parameter's (data_ptr, _version) is unchanged, and dropped by
+    `invalidate()` — which the module calls from `load_state_dict`, `_apply` (.to / .cuda / .half) and `train()`.  Code
+    that edits weights through `.data` in eval mode must call `B200ConformerEncoder.invalidate_weight_cache()` itself."""
 
     def __init__(self):
         self.store = {}
-        self.always_rebuild = False
 
     def invalidate(self):
         self.store.clear()
-
-    def get(self, key, params, build):
-        if self.always_rebuild:
-            return build()
-        ver = tuple((p.data_ptr(), p._version) for p in params)
-        hit = self.store.get(key)
-        if hit is None or hit[0] != ver:
-            self.store[key] = (ver, build())
-            hit = self.store[key]
-        return hit[1]
 
 
 def _cast(w: torch.Tensor) -> torch.Tensor:
@@ -352,47 +341,79 @@ class B200ConformerEncoder(nn.Module):
         return (torch.initial_seed() * 1000003 + self._step) & 0xFFFFFFFFFFFFFFFF
 
     # bf16 operand preparation ------------------------------------------------------------------------------------
-    def _weights(self):
-        wc, pe = self._wc, self.pre_encode
-        wc.always_rebuild = self.training
+    def _operand_plan(self, dev):
+        """Persistent operand buffers (kernel layouts) + the table that fills them from the fp32 master weights in ONE
+        launch (csrc/optim.cu: prep_weights).  entry = (param, A, B, C, dst tensor, dst element offset, sa, sb, sc, f32)."""
+        pe = self.pre_encode
         C, F2, d = pe._conv_channels, pe._f_out, self.d_model
-        W = {}
-        w1 = pe.conv[0].weight  # [C,1,3,3] → [C,16] bf16: the 9 taps, then zeros (column 9 multiplies the patch's ones)
+        W, ent = {}, []
 
-        def build_w1():
-            w16 = torch.zeros(C, 16, dtype=F32, device=w1.device)
-            w16[:, :9] = w1.detach().reshape(C, 9)
-            return _cast(w16)
+        def buf(key, *shape, dtype=BF16, zero=False):
+            W[key] = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=dev)
+            return W[key]
 
-        W["conv1"] = wc.get("conv1", [w1], build_w1)
+        def plain(param, dst, off=0, f32=False):
+            n = param.numel()
+            ent.append((param, 1, 1, n, dst, off, n, n, 1, f32))
+
+        # stem [C,1,3,3] → [C,16]: the 9 taps, then zeros (column 9 multiplies the patch's ones column; bias is added by
+        # the epilogue)
+        ent.append((pe.conv[0].weight, C, 1, 9, buf("conv1", C, 16, zero=True), 0, 16, 0, 1, False))
         if self.subsampling == "striding":
-            w2 = pe.conv[2].weight
-            W["conv2"] = wc.get("conv2", [w2], lambda: _permute_bf16(w2, C, C, 9, 1).view(C, 9 * C))       # [co, tap, ci]
-            W["conv2_d"] = wc.get("conv2_d", [w2], lambda: _permute_bf16(_permute_f32(w2, C, C, 9, 0), C, C, 9, 1).view(C, 9 * C))  # [ci, tap, co]
+            w2 = pe.conv[2].weight                                                      # [co, ci, 9]
+            ent.append((w2, C, C, 9, buf("conv2", C, 9 * C), 0, 9 * C, 1, C, False))      # → [co, tap, ci]
+            ent.append((w2, C, C, 9, buf("conv2_d", C, 9 * C), 0, 1, 9 * C, C, False))    # → [ci, tap, co]
         else:
             for i in (3, 6):
-                wpw = pe.conv[i].weight
-                W[f"pw{i}"] = wc.get(f"pw{i}", [wpw], lambda wpw=wpw: _cast(wpw).view(C, C))
-        wo = pe.out.weight
-        W["out"] = wc.get("out", [wo], lambda: _permute_bf16(wo, d, C, F2, 1).view(d, F2 * C))               # [n, f, c]
+                plain(pe.conv[i].weight, buf(f"pw{i}", C, C))
+        ent.append((pe.out.weight, d, C, F2, buf("out", d, F2 * C), 0, F2 * C, 1, C, False))  # [n, c, f] → [n, f, c]
         for i, lyr in enumerate(self.layers):
             for nm, ff in (("ff1", lyr.feed_forward1), ("ff2", lyr.feed_forward2)):
-                W[f"{i}.{nm}.w1"] = wc.get(f"{i}.{nm}.w1", [ff.linear1.weight], lambda ff=ff: _cast(ff.linear1.weight))
-                W[f"{i}.{nm}.w2"] = wc.get(f"{i}.{nm}.w2", [ff.linear2.weight], lambda ff=ff: _cast(ff.linear2.weight))
+                plain(ff.linear1.weight, buf(f"{i}.{nm}.w1", self.d_ff, d))
+                plain(ff.linear2.weight, buf(f"{i}.{nm}.w2", d, self.d_ff))
             at = lyr.self_attn
-            qkv = [at.linear_q.weight, at.linear_k.weight, at.linear_v.weight]
-            W[f"{i}.qkv"] = wc.get(f"{i}.qkv", qkv, lambda qkv=qkv: torch.cat([_cast(w) for w in qkv], 0))
-            qkvb = [at.linear_q.bias, at.linear_k.bias, at.linear_v.bias]
-            W[f"{i}.qkv_b"] = wc.get(f"{i}.qkv_b", qkvb, lambda qkvb=qkvb: torch.cat([b.detach() for b in qkvb], 0))
-            W[f"{i}.pos"] = wc.get(f"{i}.pos", [at.linear_pos.weight], lambda at=at: _cast(at.linear_pos.weight))
-            W[f"{i}.o"] = wc.get(f"{i}.o", [at.linear_out.weight], lambda at=at: _cast(at.linear_out.weight))
+            qkv, qkvb = buf(f"{i}.qkv", 3 * d, d), buf(f"{i}.qkv_b", 3 * d, dtype=F32)
+            for j, lin in enumerate((at.linear_q, at.linear_k, at.linear_v)):
+                plain(lin.weight, qkv, j * d * d)
+                plain(lin.bias, qkvb, j * d, f32=True)
+            plain(at.linear_pos.weight, buf(f"{i}.pos", d, d))
+            plain(at.linear_out.weight, buf(f"{i}.o", d, d))
             cv = lyr.conv
-            w1, b1 = cv.pointwise_conv1.weight, cv.pointwise_conv1.bias
             # GLU value/gate interleave: rows (j, j+d) of [2d, d] → rows (2j, 2j+1)
-            W[f"{i}.pw1"] = wc.get(f"{i}.pw1", [w1], lambda w1=w1: _permute_bf16(w1, 2, d, d, 0).view(2 * d, d))
-            W[f"{i}.pw1_b"] = wc.get(f"{i}.pw1_b", [b1], lambda b1=b1: _permute_f32(b1, 2, d, 1, 0).view(2 * d))
-            W[f"{i}.pw2"] = wc.get(f"{i}.pw2", [cv.pointwise_conv2.weight], lambda cv=cv: _cast(cv.pointwise_conv2.weight).view(d, d))
-        return W
+            ent.append((cv.pointwise_conv1.weight, 2, d, d, buf(f"{i}.pw1", 2 * d, d), 0, d, 2 * d, 1, False))
+            ent.append((cv.pointwise_conv1.bias, 2, d, 1, buf(f"{i}.pw1_b", 2 * d, dtype=F32), 0, 1, 2, 1, True))
+            plain(cv.pointwise_conv2.weight, buf(f"{i}.pw2", d, d))
+        return W, ent
+
+    def _weights(self):
+        params_now = None
+        plan = self.__dict__.get("_plan")
+        dev = self.pre_encode.out.weight.device
+        if plan is not None:
+            params_now = tuple(e[0].data_ptr() for e in plan["ent"])
+            if plan["ptrs"] != params_now or plan["dev"] != dev:
+                plan = None
+        if plan is None:
+            W, ent = self._operand_plan(dev)
+            entries, numels = [], []
+            for (p_, A, B_, C_, dst, off, sa, sb, sc, f32) in ent:
+                if p_.dtype != F32 or not p_.is_contiguous():
+                    raise NotImplementedError("B200ConformerEncoder keeps fp32 contiguous master parameters (autocast protocol)")
+                entries.append(L.PrepEntry(p_.data_ptr(), dst.data_ptr() + off * dst.element_size(), A, B_, C_, 2 if f32 else 0,
+                                           sa, sb, sc))
+                numels.append(A * B_ * C_)
+            tab, blocks, nb = L.upload_table(entries, numels, dev)
+            plan = dict(W=W, ent=ent, tab=tab, blocks=blocks, nb=nb, dev=dev, ptrs=tuple(e[0].data_ptr() for e in ent), ver=None)
+            self.__dict__["_plan"] = plan
+        # training: refill on every forward (nothing cheap proves the weights did not change, see _WeightCache);
+        # eval: only when a parameter version moved or the cache was invalidated
+        ver = None if self.training else tuple(e[0]._version for e in plan["ent"])
+        if self.training or plan["ver"] != ver or self._wc.store.get("valid") is not True:
+            L.check(L.lib.b2c_prep_weights(plan["tab"].data_ptr(), plan["blocks"].data_ptr(), plan["nb"], L.stream()),
+                    "b2c_prep_weights")
+            plan["ver"] = ver
+            self._wc.store["valid"] = True
+        return plan["W"]
 
     def _pos_table(self, T, dev, p_emb=0.0, seed=0):
         key = (T, str(dev))
@@ -491,6 +512,7 @@ class _EncoderFn(torch.autograd.Function):
         # ---- conformer layers ---------------------------------------------------------------------------------
         layers_saved = []
         taps = enc.__dict__.get("_debug_taps")
+        bn_stats_all = arena.zeros(enc.n_layers, 2, d)  # per-layer BatchNorm sum / sum-of-squares accumulators: one fill
         for li, lyr in enumerate(enc.layers):
             sv = {}
             site = li * 16
@@ -540,14 +562,13 @@ class _EncoderFn(torch.autograd.Function):
                   rows_per_batch=T)
             c = _empty(M, d, dev=dev)
             bn = cv.batch_norm
-            stats = arena.zeros(2, d)
+            stats = bn_stats_all[li]
             L.call("dwconv_fwd", u, cv.depthwise_conv.weight.detach(), cv.depthwise_conv.bias.detach(), c,
                    stats[0] if training else None, stats[1] if training else None, B, T, d, k)
             bnp = _empty(4, d, dtype=F32, dev=dev)  # scale, shift, mean, rstd
             L.call("bn_finalize", stats[0], stats[1], bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
-                   bnp[0], bnp[1], bnp[2], bnp[3], M, d, 1 if training else 0, bn.momentum, bn.eps)
-            if training:
-                bn.num_batches_tracked += 1
+                   bnp[0], bnp[1], bnp[2], bnp[3], M, d, 1 if training else 0, bn.momentum, bn.eps,
+                   bn.num_batches_tracked if training else None)
             s_ = _empty(M, d, dev=dev)
             L.call("bn_silu_fwd", c, bnp[0], bnp[1], s_, M, d)
             xc = _empty(M, d, dtype=F32, dev=dev)
@@ -603,13 +624,21 @@ class _EncoderFn(torch.autograd.Function):
                     raise RuntimeError(f"FlatGradients was built while '{n}' was frozen; rebuild it after unfreezing")
                 else:
                     G[n] = torch.zeros_like(p)  # frozen parameter: scratch, never read
+            gblock = fg.block
         else:
-            sizes = [p.numel() for p in plist]
-            flat = torch.zeros(sum(sizes), dtype=F32, device=dev)
-            off = 0
-            for n, p, sz in zip(names, plist, sizes):
-                G[n] = flat[off:off + sz].view_as(p)
-                off += sz
+            from .parallel import grad_layout
+            order = grad_layout(zip(names, plist))  # q|k|v weights (and biases) adjacent: see parallel.grad_layout
+            flat = torch.zeros(sum(p.numel() for _, p in order), dtype=F32, device=dev)
+            off, offs = 0, {}
+            for n, p in order:
+                G[n] = flat[off:off + p.numel()].view_as(p)
+                offs[n] = off
+                off += p.numel()
+            onames = [n for n, _ in order]
+
+            def gblock(first, count):
+                i = onames.index(first)
+                return flat[offs[first]:offs[first] + sum(order[i + k][1].numel() for k in range(count))]
 
         arena = _Arena(dev)
         _empty = arena.alloc  # noqa: F811
@@ -626,6 +655,9 @@ class _EncoderFn(torch.autograd.Function):
             """gout[N_, K_] += dy[M, N_]^T @ x_[M, K_]   (contraction over tokens, both operands MN-major)"""
             _gemm(dy, x_, N_, K_, M, L.EPI_ACCUM_F32, a_mn=1, b_mn=1, lda=N_, ldb=K_, out0=gout, ldo=K_, alpha=alpha)
 
+        # fp32 accumulators of every layer out of ONE zeroed slab (one fill kernel for the whole backward)
+        nl = enc.n_layers
+        acc_all = arena.zeros_many(*([(2, d), (2 * d, d), (2 * d,), (2 * T - 1, d)] * nl))
         for li in range(enc.n_layers - 1, -1, -1):
             lyr, sv, pfx, site = enc.layers[li], ctx.layers_saved[li], f"layers.{li}.", li * 16
             xd, m5, r5 = sv["out"]
@@ -656,7 +688,7 @@ class _EncoderFn(torch.autograd.Function):
             L.call("colsum_bf16", t16, G[pfx + "conv.pointwise_conv2.bias"], M, d, d)
             ds = _empty(M, d, dev=dev)
             _gemm(t16, W[f"{li}.pw2"], M, d, d, L.EPI_BF16, b_mn=1, ldb=d, out0=ds)
-            sums, gw, gb, dpos, gqkv, gqb = arena.zeros_many((2, d), (2 * d, d), (2 * d,), (2 * T - 1, d), (3 * d, d), (3 * d,))
+            sums, gw, gb, dpos = acc_all[4 * li:4 * li + 4]
             L.call("bn_silu_bwd_reduce", ds, c, bnp[0], bnp[1], bnp[2], bnp[3], sums[0], sums[1], M, d)
             dc = _empty(M, d, dev=dev)
             L.call("bn_silu_bwd_apply", ds, c, cv.batch_norm.weight.detach(), bnp[0], bnp[1], bnp[2], bnp[3], sums[0],
@@ -690,11 +722,18 @@ class _EncoderFn(torch.autograd.Function):
             L.call("relpos_attn_bwd", qkv, pp, at.pos_bias_u.detach(), at.pos_bias_v.detach(), mt["lens"][-1], ctxv, ctx32, dctx, lse,
                    dqkv, dpos, G[pfx + "self_attn.pos_bias_u"], G[pfx + "self_attn.pos_bias_v"], ws, nbytes, B, T, H, dk,
                    p_att, seed, site + S_ATT_P)
-            wgrad(dqkv, 3 * d, y2, d, gqkv)
+            # the fused q|k|v projection's gradients land directly in the adjacent linear_q/k/v slices of the flat buffer
+            gqkv = gblock(pfx + "self_attn.linear_q.weight", 3)
+            gqb = gblock(pfx + "self_attn.linear_q.bias", 3)
+            direct = gqkv is not None and gqb is not None and gqkv.numel() == 3 * d * d and gqb.numel() == 3 * d
+            if not direct:  # some of q/k/v frozen: scratch + scatter-add
+                gqkv, gqb = arena.zeros_many((3 * d, d), (3 * d,))
+            wgrad(dqkv, 3 * d, y2, d, gqkv.view(3 * d, d))
             L.call("colsum_bf16", dqkv, gqb, M, 3 * d, 3 * d)
-            for j, nm in enumerate(("linear_q", "linear_k", "linear_v")):
-                G[f"{pfx}self_attn.{nm}.weight"].add_(gqkv[j * d:(j + 1) * d])
-                G[f"{pfx}self_attn.{nm}.bias"].add_(gqb[j * d:(j + 1) * d])
+            if not direct:
+                for j, nm in enumerate(("linear_q", "linear_k", "linear_v")):
+                    G[f"{pfx}self_attn.{nm}.weight"].add_(gqkv.view(3 * d, d)[j * d:(j + 1) * d])
+                    G[f"{pfx}self_attn.{nm}.bias"].add_(gqb[j * d:(j + 1) * d])
             dpos16 = _empty(2 * T - 1, d, dev=dev)
             L.call("cast_bf16", dpos, dpos16, dpos.numel(), 1.0)
             _gemm(dpos16, mt["pos16"], d, d, 2 * T - 1, L.EPI_ACCUM_F32, a_mn=1, b_mn=1, lda=d, ldb=d,

@@ -20,6 +20,31 @@ import torch
 import torch.distributed as dist
 
 
+def grad_layout(named_params):
+    """Order of the parameters inside the flat gradient buffer: `named_parameters()` order, except that inside every
+    self-attention block linear_q / linear_k / linear_v weights (and biases) are adjacent — the fused q|k|v projection's
+    weight gradient [3d, d] (and bias gradient [3d]) is then ONE GEMM output written in place, with no scatter-adds.
+    Returns [(name, param)]; every layer's parameters stay contiguous (per-layer all-reduce spans)."""
+    items = list(named_params)
+    out, i = [], 0
+    while i < len(items):
+        n = items[i][0]
+        if n.endswith("self_attn.linear_q.weight"):
+            pfx = n[: -len("linear_q.weight")]
+            want = [pfx + "linear_q.weight", pfx + "linear_q.bias", pfx + "linear_k.weight", pfx + "linear_k.bias",
+                    pfx + "linear_v.weight", pfx + "linear_v.bias"]
+            got = [x[0] for x in items[i:i + 6]]
+            if got == want:
+                blk = dict(items[i:i + 6])
+                for k in (0, 2, 4, 1, 3, 5):
+                    out.append((want[k], blk[want[k]]))
+                i += 6
+                continue
+        out.append(items[i])
+        i += 1
+    return out
+
+
 class FlatGradients:
     """Owns the flat gradient buffer of a module and the layer-wise overlapped all-reduce."""
 
@@ -27,7 +52,7 @@ class FlatGradients:
         self.module = module
         self.group = process_group
         self.defer = defer
-        params = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        params = grad_layout((n, p) for n, p in module.named_parameters() if p.requires_grad)
         self.names = [n for n, _ in params]
         self.sizes = [p.numel() for _, p in params]
         dev = params[0][1].device
@@ -64,6 +89,14 @@ class FlatGradients:
     def view(self, name: str) -> torch.Tensor:
         lo, hi = self.offsets[name]
         return self.flat[lo:hi]
+
+    def block(self, first: str, count: int):
+        """flat view covering `count` consecutive parameters starting at `first` (None unless they are adjacent)"""
+        i = self.names.index(first) if first in self.offsets else -1
+        if i < 0 or i + count > len(self.names):
+            return None
+        lo, hi = self.offsets[self.names[i]][0], self.offsets[self.names[i + count - 1]][1]
+        return self.flat[lo:hi] if hi - lo == sum(self.sizes[i:i + count]) else None
 
     def span(self, prefix: str):
         los = [v[0] for k, v in self.offsets.items() if k.startswith(prefix)]

@@ -341,6 +341,20 @@ def ctc_head(sd, x: torch.Tensor, prefix="decoder_layers.0."):
 # ----------------------------------------------------------------------------------------------
 # SpecAugment (training-time masking between the front-end and the encoder)
 # ----------------------------------------------------------------------------------------------
+def ctc_loss(log_probs: torch.Tensor, targets: torch.Tensor, input_lengths: torch.Tensor, target_lengths: torch.Tensor,
+             blank: int, reduction: str = "mean_batch") -> torch.Tensor:
+    """CTCLoss.forward — nemo/collections/asr/losses/ctc.py:44-82: log_probs [B,T,V+1] → transpose to [T,B,V+1] →
+    torch.nn.CTCLoss(blank=num_classes, reduction='none', zero_infinity=False), then 'mean_batch' = losses.mean()
+    (:57-60), 'mean_volume' = losses.sum() / target_lengths.sum().  The alpha recursion itself is torch's (third party)."""
+    losses = F.ctc_loss(log_probs.transpose(1, 0), targets.long(), input_lengths.long(), target_lengths.long(), blank=blank,
+                        reduction="none", zero_infinity=False)
+    if reduction == "mean_batch":
+        return losses.mean()
+    if reduction == "mean_volume":
+        return losses.sum() / target_lengths.sum()
+    return losses
+
+
 def spec_augment_vectorized(spec: torch.Tensor, length: torch.Tensor, freq_masks: int, time_masks: int, freq_width: int,
                             time_width, mask_value: float = 0.0) -> torch.Tensor:
     """SpecAugment._forward_vectorized / _apply_masks (spectr_augment.py:135-215): time masks first, then frequency

@@ -245,6 +245,33 @@ def load():
         sys.modules[name] = m
         spec.loader.exec_module(m)
         ns.SpecAugment = m.SpecAugment
+    # CTC head: ConvASRDecoder lives in conv_asr.py next to the Jasper encoder, so jasper.py and
+    # tdnn_attention.py are exec'd too (unmodified); only the adapter mixin needs a stub class
+    rels = ["nemo/collections/asr/parts/submodules/jasper.py", "nemo/collections/asr/parts/submodules/tdnn_attention.py",
+            "nemo/collections/asr/modules/conv_asr.py"]
+    if all(os.path.exists(os.path.join(REF_ROOT, r)) for r in rels):
+
+        class _AdapterModuleMixin:
+            def set_accepted_adapter_types(self, *_a, **_k):
+                pass
+
+            def is_adapter_available(self):
+                return False
+
+        am = _mod("nemo.core.classes.mixins.adapter_mixins", AdapterModuleMixin=_AdapterModuleMixin,
+                  get_registered_adapter=lambda cls: True, register_adapter=lambda **k: None)
+        sys.modules["nemo.core.classes.mixins"].adapter_mixins = am
+        om = sys.modules["omegaconf"]
+        for nm in ("MISSING", "OmegaConf"):
+            if not hasattr(om, nm):
+                setattr(om, nm, "???" if nm == "MISSING" else type("OmegaConf", (), {}))
+        for rel in rels:
+            name = rel[:-3].replace("/", ".")
+            spec = importlib.util.spec_from_file_location(name, os.path.join(REF_ROOT, rel))
+            m = importlib.util.module_from_spec(spec)
+            sys.modules[name] = m
+            spec.loader.exec_module(m)
+        ns.ConvASRDecoder = sys.modules["nemo.collections.asr.modules.conv_asr"].ConvASRDecoder
     _loaded = ns
     return ns
 

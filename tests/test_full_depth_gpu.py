@@ -132,8 +132,8 @@ def test_dither_is_gaussian_seeded_and_train_only():
     # mel[m] = sigma^2 * sum(w^2) * sum_k fb[m,k]; compare the time-averaged linear mel energies with that expectation.
     sig = 1e-2
     pre2 = B200MelPreprocessor(window_size=0.025, window_stride=0.01, features=80, n_fft=512, dither=sig, pad_to=0, preemph=0.0).to(DEV).train()
-    z = torch.zeros(2, 16000 * 20, device=DEV)
-    zl = torch.full((2,), z.shape[1], dtype=torch.int64, device=DEV)
+    z = torch.zeros(4, 16000 * 60, device=DEV)
+    zl = torch.full((4,), z.shape[1], dtype=torch.int64, device=DEV)
     raw, rl = pre2.featurizer.forward_raw(z, zl)
     lin = (raw[:, :, 2:-3].exp() - 2 ** -24).mean(dim=(0, 2))  # interior frames only (no edge padding)
     w = pre2.featurizer.window.double()

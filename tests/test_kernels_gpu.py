@@ -252,7 +252,7 @@ def test_conv_module_core(B, T, d, k):
     rm, rv = 0.1 * rnd(d, seed=6), 1 + 0.1 * rnd(d, seed=7).abs()
     rm0, rv0 = rm.clone(), rv.clone()
     scale, shift, mean, rstd = (torch.empty(d, device=DEV) for _ in range(4))
-    L.call("bn_finalize", ssum, ssq, gamma, beta, rm, rv, scale, shift, mean, rstd, M, d, 1, 0.1, 1e-5)
+    L.call("bn_finalize", ssum, ssq, gamma, beta, rm, rv, scale, shift, mean, rstd, M, d, 1, 0.1, 1e-5, None)
     bm, bv = cq.mean((0, 1)), cq.var((0, 1), unbiased=False)
     report("bn_mean", mean, bm, 1e-3)
     report("bn_rstd", rstd, torch.rsqrt(bv + 1e-5), 1e-3)

@@ -147,3 +147,31 @@ def test_golden_spec_augment(golden_dir, tag, time_width):
     assert np.array_equal((got == 0).numpy(), z[f"vec_{tag}"])
     got = O.spec_augment_legacy(x, ln, random.Random(3), 2, 5, 27, time_width)
     assert np.array_equal((got == 0).numpy(), z[f"legacy_{tag}"])
+
+
+@needs_ref
+def test_live_reference_ctc_head():
+    """O.ctc_head against the exec'd reference ConvASRDecoder (conv_asr.py:407-468): bit-identical log-probs."""
+    ref = rl.load()
+    torch.manual_seed(0)
+    dec = ref.ConvASRDecoder(feat_in=48, num_classes=37)
+    x = torch.randn(2, 48, 29)
+    want = dec(encoder_output=x)
+    got = O.ctc_head(dec.state_dict(), x)
+    assert list(dec.state_dict().keys()) == ["decoder_layers.0.weight", "decoder_layers.0.bias"]
+    assert torch.equal(want, got)
+
+
+def test_golden_ctc_head_and_loss(golden_dir):
+    """fixture from the unmodified reference (tools/make_golden.py::gen_ctc_head): head log-probs, CTC loss and gradients"""
+    z, sd = _load(golden_dir, "ctc_head.npz")
+    x = torch.from_numpy(z["x"]).requires_grad_(True)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    lp = O.ctc_head(sdr, x)
+    assert torch.equal(lp.detach(), torch.from_numpy(z["logp"]))
+    losses = O.ctc_loss(lp, torch.from_numpy(z["tgt"]), torch.from_numpy(z["in_len"]), torch.from_numpy(z["tgt_len"]), blank=30,
+                        reduction="none")
+    assert np.allclose(losses.detach().numpy(), z["losses"], rtol=1e-6, atol=1e-6)
+    losses.mean().backward()
+    assert np.allclose(x.grad.numpy(), z["dx"], rtol=1e-5, atol=1e-7)
+    assert np.allclose(sdr["decoder_layers.0.weight"].grad.numpy(), z["dW"], rtol=1e-5, atol=1e-6)

@@ -134,7 +134,34 @@ def gen_encoder_cuda_cfg():
                             cfg=np.array(repr(c)), **grads, **bn)
 
 
+def gen_ctc_head():
+    """ConvASRDecoder (conv_asr.py:407-468) + CTCLoss (losses/ctc.py:25-82; its arithmetic is torch.nn.CTCLoss) of the
+    unmodified reference: log-probs, loss (mean_batch) and gradients for a small ragged batch."""
+    ref = rl.load()
+    torch.manual_seed(3)
+    dec = ref.ConvASRDecoder(feat_in=64, num_classes=30)
+    with torch.no_grad():
+        dec.decoder_layers[0].bias.normal_(0, 0.1)
+    x = torch.randn(3, 64, 41, requires_grad=True)
+    lp = dec(encoder_output=x)
+    in_len = torch.tensor([41, 33, 12])
+    tgt_len = torch.tensor([9, 5, 4])
+    tgt = torch.randint(0, 30, (3, 9))
+    tgt[0, 3] = tgt[0, 2]  # a repeated label (needs the blank between)
+    # CTCLoss.forward, losses/ctc.py:70-82, reduction 'mean_batch' (:57-60): torch CTC with blank = num_classes, then mean
+    losses = torch.nn.functional.ctc_loss(lp.transpose(1, 0), tgt.long(), in_len.long(), tgt_len.long(), blank=30,
+                                          reduction="none", zero_infinity=False)
+    loss = losses.mean()
+    loss.backward()
+    np.savez_compressed(os.path.join(OUT, "ctc_head.npz"), x=x.detach().numpy(), logp=lp.detach().numpy(),
+                        in_len=in_len.numpy(), tgt_len=tgt_len.numpy(), tgt=tgt.numpy(), losses=losses.detach().numpy(),
+                        loss=loss.detach().numpy(), dx=x.grad.numpy(),
+                        dW=dec.decoder_layers[0].weight.grad.numpy(), db=dec.decoder_layers[0].bias.grad.numpy(),
+                        **sd_np(dec.state_dict()))
+
+
 if __name__ == "__main__":
+    gen_ctc_head()
     gen_encoder_cuda_cfg()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
