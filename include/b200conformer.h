@@ -208,6 +208,41 @@ int b2c_relpos_table(void* pos_bf16, float* pos_f32, int T, int d, void* stream)
 int b2c_subsample_lengths(const int64_t* len_in, int32_t* len_in32, int32_t* len_stage, int64_t* len_out64, int B,
                           int n_convs, void* stream);
 
+/* ------------------------------------------------------------------------------------------------ fp32 parity mode
+ * Forward pass with fp32-accurate arithmetic (SURVEY.md §8c policy (i)): contractions stay on b2c_gemm — each fp32 operand is
+ * split into bf16 hi + lo (b2c_p_split2) and A·B accumulates hi·hi + hi·lo + lo·hi through B2C_EPI_ACCUM_F32 into an fp32
+ * output pre-filled with the bias (b2c_p_fill_rows) — and the ops between them are the plain fp32 kernels below (fp32 in,
+ * fp32 out, exact expf sigmoid).  `nemo_b200.B200ConformerEncoder(precision="fp32")` orchestrates them. */
+int b2c_p_split2(const float* x, void* hi_bf16, void* lo_bf16, long long n, void* stream);
+int b2c_p_fill_rows(float* out, const float* bias, long long M, int N, long long ldo, void* stream);
+/* mode 0: out = silu(a); 1: out = a + alpha*b (a may be NULL); 2: GLU of a [M,2N] (value | gate) * (t < len);
+ * 3: relu(a) * (t < len); 4: out = a + b[n] (row vector).  `a` has row pitch lda; t = (m % rows_per_batch) / rows_inner. */
+int b2c_p_pointwise(int mode, const float* a, const float* b, float* out, long long M, int N, long long lda, float alpha,
+                    const int32_t* lengths, int rows_per_batch, int rows_inner, void* stream);
+int b2c_p_bn_silu(const float* c, const float* scale, const float* shift, float* out, long long M, int N, void* stream);
+int b2c_p_colstats(const float* x, float* sum, float* sumsq, long long M, int N, void* stream);
+int b2c_p_im2col_mel(const float* mel, const int32_t* len_in, float* out, int B, int F, int T, void* stream);
+int b2c_p_im2col_nhwc(const float* x, float* out, int B, int T1, int F1, int C, void* stream);
+int b2c_p_dwconv2d(const float* x, const float* w, const float* bias, const int32_t* len_out, float* out, int B, int T1, int F1,
+                   int C, void* stream);
+int b2c_p_dwconv1d(const float* u, const float* w, const float* bias, float* out, int B, int T, int d, int k, void* stream);
+/* P[bh,i,:] = masked softmax_j(scale * (AC[bh,i,j] + R[bh,i,T-1-i+j])) with the reference's -1e4 / 0 double mask */
+int b2c_p_log_softmax(const float* logits, int ld, float* out, long long M, int V, void* stream);
+int b2c_p_attn_softmax(const float* AC, const float* R, const int32_t* lengths, float* P, int B, int H, int T, int Tp, int Rp,
+                       float scale, void* stream);
+
+/* CTC loss (nemo/collections/asr/losses/ctc.py:25-82 = torch.nn.CTCLoss(blank=num_classes, reduction='none')): log-space
+ * alpha / beta recursions, one CTA per utterance.  logp [B,T,V1] f32 (ConvASRDecoder layout), targets [B,Umax] i64 (padded),
+ * in_len / tgt_len [B] i64.  Forward keeps log_alpha [B,T,2*Umax+1] in `alpha_ws` (b2c_ctc_workspace bytes) and writes the
+ * per-utterance negative log-likelihood; backward writes dlogp [B,T,V1] = grad_out[b] * (exp(lp) - posterior), zero beyond
+ * in_len (and everywhere for infeasible utterances when zero_infinity). */
+size_t b2c_ctc_workspace(int B, int T, int Umax);
+int b2c_ctc_loss_fwd(const float* logp, const int64_t* targets, const int64_t* in_len, const int64_t* tgt_len, float* alpha_ws,
+                     float* nll, int B, int T, int V1, int Umax, int blank, void* stream);
+int b2c_ctc_loss_bwd(const float* logp, const int64_t* targets, const int64_t* in_len, const int64_t* tgt_len,
+                     const float* alpha_ws, const float* nll, const float* grad_out, float* dlogp, int B, int T, int V1, int Umax,
+                     int blank, int zero_infinity, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ training-step runtime
  * Device-side RNG counter: every dropout / dither key becomes `seed + *counter * golden-ratio`, so a CUDA-graph replay of a
  * captured step (whose by-value seeds are frozen) still draws fresh masks each step.  b2c_set_seed_counter registers the

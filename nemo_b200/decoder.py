@@ -64,6 +64,7 @@ class B200ConvASRDecoder(nn.Module):
         if init_mode == "xavier_uniform":
             nn.init.xavier_uniform_(self.decoder_layers[0].weight, gain=1.0)
         self.temperature = 1.0
+        self.precision = "bf16"  # "fp32": forward-only parity mode (nemo_b200/parity.py), fp32-equivalent logits
 
     @classmethod
     def from_reference(cls, ref):
@@ -85,4 +86,16 @@ class B200ConvASRDecoder(nn.Module):
         if self.temperature != 1.0:
             raise NotImplementedError("temperature != 1.0")
         conv = self.decoder_layers[0]
+        if self.precision == "fp32":
+            from .parity import _linear
+
+            with torch.no_grad():
+                B, D, T = encoder_output.shape
+                V = conv.weight.shape[0]
+                x = encoder_output.detach().transpose(1, 2).contiguous().to(F32).view(B * T, D)
+                logits = _linear(x, conv.weight, conv.bias, B * T, V, D)
+                logp = torch.empty(B * T, V, dtype=F32, device=x.device)
+                L.call("p_log_softmax", logits, V, logp, B * T, V)
+                self._last_logits = logits.view(B, T, V)  # pre-softmax logits (north_star's metric names them)
+                return logp.view(B, T, V)
         return _CTCHeadFn.apply(encoder_output, conv.weight, conv.bias)

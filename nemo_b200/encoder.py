@@ -252,6 +252,9 @@ class B200ConformerEncoder(nn.Module):
         self.pre_encode = _ConvSubsampling(subsampling, subsampling_factor, feat_in, d_model, conv_channels)
         self.layers = nn.ModuleList(_ConformerLayer(d_model, self.d_ff, n_heads, conv_kernel_size) for _ in range(n_layers))
         self.out_proj = None
+        # "bf16" = speed mode (the reference under torch.autocast(bfloat16)); "fp32" = forward-only parity mode with
+        # fp32-equivalent arithmetic (nemo_b200/parity.py), for validation against the fp32 reference at <= 1e-3
+        self.precision = "bf16"
         self._wc = _WeightCache()
         self._step = 0
         self._pos_cache = {}
@@ -332,6 +335,12 @@ class B200ConformerEncoder(nn.Module):
                                       "torch.no_grad(), audio_preprocessing.py:94)")
         if length is None:
             length = audio_signal.new_full((audio_signal.size(0),), audio_signal.size(-1), dtype=torch.int64)
+        if self.precision == "fp32":
+            from .parity import forward_fp32
+
+            return forward_fp32(self, audio_signal, length)
+        if self.precision != "bf16":
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {self.precision!r}")
         params = [p for _, p in self.named_parameters()]
         out, out_len = _EncoderFn.apply(self, audio_signal, length, *params)
         return out, out_len

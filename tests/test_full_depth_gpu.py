@@ -142,3 +142,85 @@ def test_dither_is_gaussian_seeded_and_train_only():
     print("dither: mel-energy / expectation: min %.3f max %.3f mean %.4f" % (ratio.min(), ratio.max(), ratio.mean()))
     assert (ratio - 1).abs().max().item() < 0.05  # ~4000 frames x several bins per filter: < 5 % sampling error
     assert abs(ratio.mean().item() - 1) < 0.01
+
+
+@pytest.mark.parametrize("name", ["cfg2_conformer_ctc_large_18L", "cfg3_fastconformer_large_17L", "cfg4_conformer_transducer_xl_24L"])
+def test_parity_mode_logits_within_1e3_of_fp32_reference(name):
+    """north_star: "encoder logits matching the reference to <= 1e-3 relative".  precision='fp32' (parity mode: tcgen05 GEMMs on
+    bf16 hi/lo-split operands = fp32-equivalent products, fp32 everywhere else) on the FULL-DEPTH BASELINE encoders, ragged
+    2 x 30 s, through the CTC head, against the fp32 oracle: rel-L2 and max-abs/max|y| <= 1e-3 for the encoder output, the
+    logits and every layer tap; log-probs <= 1e-3 absolute... (speed mode's numbers are printed next to them)."""
+    from nemo_b200.decoder import B200ConvASRDecoder
+
+    cfg, B = FULL[name]
+    sd = O.init_state_dict(seed=11, **cfg)
+    enc = B200ConformerEncoder(feat_in=80, n_layers=cfg["n_layers"], d_model=cfg["d_model"], n_heads=cfg["n_heads"],
+                               conv_kernel_size=cfg["conv_kernel_size"], subsampling=cfg["subsampling_kind"],
+                               subsampling_factor=cfg["subsampling_factor"], subsampling_conv_channels=cfg["subsampling_conv_channels"])
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.to(DEV).eval()
+    torch.manual_seed(1)
+    head = B200ConvASRDecoder(feat_in=cfg["d_model"], num_classes=1024).to(DEV)
+    sd = {k: v.to(DEV) for k, v in sd.items()}
+    with torch.no_grad():  # BatchNorm running statistics as a trained checkpoint has them (not the 0 / 1 init)
+        for i in range(cfg["n_layers"]):
+            bn = enc.layers[i].conv.batch_norm
+            bn.running_mean.normal_(0, 0.1)
+            bn.running_var.uniform_(0.75, 1.25)
+            sd[f"layers.{i}.conv.batch_norm.running_mean"] = bn.running_mean.clone()
+            sd[f"layers.{i}.conv.batch_norm.running_var"] = bn.running_var.clone()
+    pre = B200MelPreprocessor(window_size=0.025, window_stride=0.01, features=80, n_fft=512, pad_to=0).to(DEV).eval()
+    wav, wlen = O.synthetic_waveforms(B, 30.0, ragged=True)
+    if B > 1:
+        wlen[-1] = 30 * 16000 - 160 * 411
+    mel, mlen = pre(input_signal=wav.to(DEV), length=wlen.to(DEV))
+    kw = dict(n_layers=cfg["n_layers"], d_model=cfg["d_model"], n_heads=cfg["n_heads"], subsampling_kind=cfg["subsampling_kind"],
+              subsampling_factor=cfg["subsampling_factor"], training=False)
+    with torch.no_grad():
+        y_ref, ylen_ref, t_ref = O.encoder_forward(sd, mel, mlen, return_layers=True, **kw)
+        hsd = {k: v.detach() for k, v in head.state_dict().items()}
+        logits_ref = torch.nn.functional.conv1d(y_ref, hsd["decoder_layers.0.weight"], hsd["decoder_layers.0.bias"]).transpose(1, 2)
+        lp_ref = O.ctc_head(hsd, y_ref)
+        y16, _ = enc(audio_signal=mel, length=mlen)
+        lp16 = head(encoder_output=y16)
+    enc.precision = head.precision = "fp32"
+    enc.__dict__["_debug_taps"] = taps = []
+    y, ylen = enc(audio_signal=mel, length=mlen)
+    enc.__dict__["_debug_taps"] = None
+    lp = head(encoder_output=y)
+    logits = head._last_logits
+    assert torch.equal(ylen, ylen_ref)
+    relmax = lambda a, b: ((a.float() - b.float()).abs().max() / b.float().abs().max()).item()  # noqa: E731
+    for i in (0, 3, 7, 11, cfg["n_layers"] - 1):
+        print(f"[parity {name}] depth {i + 1:2d}: rel-L2 {rel_l2(taps[i], t_ref[i]):.3e}  max-abs/max|y| {relmax(taps[i], t_ref[i]):.3e}")
+    print(f"[parity {name}] encoder out: fp32 mode rel-L2 {rel_l2(y, y_ref):.3e} max-rel {relmax(y, y_ref):.3e} | speed mode rel-L2 {rel_l2(y16, y_ref):.3e}")
+    print(f"[parity {name}] logits     : fp32 mode rel-L2 {rel_l2(logits, logits_ref):.3e} max-rel {relmax(logits, logits_ref):.3e}")
+    print(f"[parity {name}] log-probs  : fp32 mode max-abs {(lp - lp_ref).abs().max().item():.3e} | speed mode {(lp16 - lp_ref).abs().max().item():.3e}")
+    for i in range(cfg["n_layers"]):
+        assert rel_l2(taps[i], t_ref[i]) <= 1e-3 and relmax(taps[i], t_ref[i]) <= 1e-3, f"layer {i}"
+    assert rel_l2(y, y_ref) <= 1e-3 and relmax(y, y_ref) <= 1e-3
+    assert rel_l2(logits, logits_ref) <= 1e-3 and relmax(logits, logits_ref) <= 1e-3
+    assert (lp - lp_ref).abs().max().item() <= 1e-3 * lp_ref.abs().max().item()
+
+
+def test_parity_mode_train_statistics_and_guards():
+    """parity mode with BatchNorm batch statistics (train(), dropout 0) on a ragged small batch; dropout > 0 is refused"""
+    cfg = dict(n_layers=2, d_model=128, n_heads=2, conv_kernel_size=9, subsampling_kind="striding", subsampling_factor=4)
+    sd = O.init_state_dict(seed=5, **cfg)
+    enc = B200ConformerEncoder(feat_in=80, n_layers=2, d_model=128, n_heads=2, conv_kernel_size=9, dropout=0.0, dropout_pre_encoder=0.0,
+                               dropout_emb=0.0, dropout_att=0.0)
+    enc.load_state_dict(sd)
+    enc = enc.to(DEV).train()
+    enc.precision = "fp32"
+    x = torch.randn(3, 80, 203, generator=torch.Generator().manual_seed(3))
+    ln = torch.tensor([203, 152, 40])
+    for b in range(3):
+        x[b, :, ln[b]:] = 0
+    y, yl = enc(audio_signal=x.to(DEV), length=ln.to(DEV))
+    y_ref, yl_ref = O.encoder_forward({k: v.to(DEV) for k, v in sd.items()}, x.to(DEV), ln.to(DEV), n_layers=2, d_model=128, n_heads=2,
+                                      training=True)
+    print(f"[parity train-BN] rel-L2 {rel_l2(y, y_ref):.3e}")
+    assert torch.equal(yl, yl_ref) and rel_l2(y, y_ref) <= 1e-3
+    enc.dropout = 0.1
+    with pytest.raises(NotImplementedError):
+        enc(audio_signal=x.to(DEV), length=ln.to(DEV))

@@ -185,3 +185,78 @@ def test_spec_augment_host_draws_match_the_oracle(time_width):
     want = O.spec_augment_legacy(x, ln, random.Random(3), 2, 5, 27, time_width) == 0
     got = mask_from(torch.tensor(ts), torch.tensor(te), torch.tensor(fs), torch.tensor(fe))
     assert torch.equal(got, want)
+
+
+def test_nemo_checkpoint_round_trip(tmp_path):
+    """.nemo import / export (save_restore_connector.py:44-45,599-607,700-759): a reference-layout checkpoint — written here
+    exactly the way `_make_nemo_file_from_folder` does (tar 'w:', arcname '.') from live reference modules when
+    /root/reference is present, else from oracle-initialised weights — loads into the B200 modules, and what `save_nemo`
+    writes has the reference's member names / key layout and loads back bit-identically (also from a gzip'ed tar)."""
+    import tarfile
+
+    import yaml
+
+    from nemo_b200 import checkpoint as ck
+    from nemo_b200.decoder import B200ConvASRDecoder
+    from nemo_b200.encoder import B200ConformerEncoder
+    from nemo_b200.preprocessor import B200MelPreprocessor
+    from oracle import conformer_oracle as O
+    from oracle import ref_loader as rl
+
+    enc_cfg = dict(feat_in=80, n_layers=2, d_model=128, n_heads=2, conv_kernel_size=9, subsampling="striding", subsampling_factor=4,
+                   subsampling_conv_channels=-1, dropout=0.1, dropout_pre_encoder=0.1, dropout_emb=0.0, dropout_att=0.1)
+    if rl.available():
+        ref = rl.load()
+        enc_ref = rl.make_encoder(seed=3, **enc_cfg)
+        dec_ref = ref.ConvASRDecoder(feat_in=128, num_classes=64)
+        fb_ref = ref.FilterbankFeatures(sample_rate=16000, n_window_size=400, n_window_stride=160, n_fft=512, nfilt=80, dither=1e-5, pad_to=0)
+        sd = {f"encoder.{k}": v for k, v in enc_ref.state_dict().items()}
+        sd.update({f"decoder.{k}": v for k, v in dec_ref.state_dict().items()})
+        sd.update({f"preprocessor.featurizer.{k}": v for k, v in fb_ref.state_dict().items()})
+    else:
+        sd = {f"encoder.{k}": v for k, v in O.init_state_dict(seed=3, n_layers=2, d_model=128, n_heads=2, conv_kernel_size=9).items()}
+        sd["decoder.decoder_layers.0.weight"] = torch.randn(65, 128, 1)
+        sd["decoder.decoder_layers.0.bias"] = torch.randn(65)
+    conf = {"sample_rate": 16000, "encoder": dict(enc_cfg, _target_="nemo.collections.asr.modules.ConformerEncoder"),
+            "decoder": {"_target_": "nemo.collections.asr.modules.ConvASRDecoder", "feat_in": 128, "num_classes": 64}}
+    src = tmp_path / "src"
+    src.mkdir()
+    torch.save(sd, src / "model_weights.ckpt")
+    (src / "model_config.yaml").write_text(yaml.safe_dump(conf))
+    ref_file = str(tmp_path / "ref.nemo")
+    with tarfile.open(ref_file, "w:") as tar:  # save_restore_connector.py:605-606
+        tar.add(str(src), arcname=".")
+    cfg, got = ck.load_nemo(ref_file)
+    assert cfg["encoder"]["d_model"] == 128 and set(got) == set(sd)
+    enc = ck.encoder_from_config(cfg["encoder"])
+    dec = B200ConvASRDecoder(feat_in=128, num_classes=64)
+    pre = B200MelPreprocessor(window_size=0.025, window_stride=0.01, features=80, n_fft=512, pad_to=0)
+    ck.restore(ref_file, preprocessor=pre if rl.available() else None, encoder=enc, decoder=dec)
+    for k, v in enc.state_dict().items():
+        assert torch.equal(v, sd[f"encoder.{k}"]), k
+    assert torch.equal(dec.state_dict()["decoder_layers.0.weight"], sd["decoder.decoder_layers.0.weight"])
+    ours = ck.save_nemo(str(tmp_path / "ours.nemo"), conf, preprocessor=pre, encoder=enc, decoder=dec)
+    with tarfile.open(ours, "r:") as tar:
+        names = sorted(m.name for m in tar.getmembers())
+    with tarfile.open(ref_file, "r:") as tar:
+        ref_names = sorted(m.name for m in tar.getmembers())
+    assert names == ref_names == [".", "./model_config.yaml", "./model_weights.ckpt"]
+    cfg2, sd2 = ck.load_nemo(ours)
+    assert cfg2 == cfg
+    assert [k for k in sd2 if k.startswith("encoder.")] == [k for k in sd if k.startswith("encoder.")]  # key ORDER too
+    for k in sd:
+        if k.startswith(("encoder.", "decoder.")):
+            assert torch.equal(sd2[k], sd[k]), k
+    if rl.available():  # what we wrote loads into the unmodified reference modules, strictly
+        parts = ck.split_state_dict(sd2)
+        enc_ref.load_state_dict(parts["encoder"], strict=True)
+        dec_ref.load_state_dict(parts["decoder"], strict=True)
+    gz = str(tmp_path / "old.nemo")
+    with tarfile.open(gz, "w:gz") as tar:  # pre-1.7 checkpoints are gzip'ed
+        tar.add(str(src), arcname=".")
+    assert set(ck.load_nemo(gz)[1]) == set(sd)
+    evil = str(tmp_path / "evil.nemo")
+    with tarfile.open(evil, "w:") as tar:
+        tar.add(str(src / "model_weights.ckpt"), arcname="../model_weights.ckpt")
+    with pytest.raises(FileNotFoundError):
+        ck.load_nemo(evil)

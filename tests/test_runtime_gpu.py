@@ -129,7 +129,9 @@ def test_seed_counter_changes_masks_and_captured_step_equals_eager():
         enc = _enc(p=0.1)
         enc._seed = lambda: 1234  # freeze the by-value seed exactly as a captured graph does
         fg = FlatGradients(enc)
-        opt = B200FusedAdamW(fg, lr=1e-3, betas=(0.9, 0.98), weight_decay=1e-3)
+        # eps = 1: the update is ~lr * m (SGD-like).  With Adam's default eps a parameter whose gradient is rounding noise
+        # (analytically zero: depthwise_conv.bias under BatchNorm) moves by +-lr with a random sign, in eager and captured alike
+        opt = B200FusedAdamW(fg, lr=1e-2, betas=(0.9, 0.98), eps=1.0, weight_decay=1e-3)
         return enc, fg, opt
 
     enc, fg, opt = make()
@@ -168,3 +170,59 @@ def test_seed_counter_changes_masks_and_captured_step_equals_eager():
     print("captured vs eager weights after 3 steps: worst rel-L2", worst)
     assert worst < 1e-3  # split-K atomics reorder fp32 sums; everything else is identical
     ctr.zero_()
+
+
+@pytest.mark.parametrize("reduction", ["mean_batch", "mean_volume", "none"])
+def test_ctc_loss_vs_oracle(reduction):
+    """B200CTCLoss (csrc/ctc.cu) against the oracle restatement of nemo/collections/asr/losses/ctc.py (torch CTC on CPU, fp32):
+    ragged inputs, repeated labels, an empty target and a BPE-sized vocabulary."""
+    from nemo_b200.losses import B200CTCLoss
+
+    g = torch.Generator().manual_seed(9)
+    B, T, V = 5, 188, 1024
+    logits = torch.randn(B, T, V + 1, generator=g)
+    in_len = torch.tensor([188, 150, 97, 40, 188])
+    tgt_len = torch.tensor([60, 33, 20, 0, 7])
+    tgt = torch.randint(0, V, (B, 60), generator=g)
+    tgt[0, 10:14] = tgt[0, 10]  # repeated labels
+    x = logits.to(DEV).requires_grad_(True)
+    lp = torch.log_softmax(x, dim=-1)
+    loss = B200CTCLoss(num_classes=V, reduction=reduction)(log_probs=lp, targets=tgt.to(DEV), input_lengths=in_len.to(DEV),
+                                                           target_lengths=tgt_len.to(DEV))
+    xr = logits.clone().requires_grad_(True)
+    ref = O.ctc_loss(torch.log_softmax(xr, dim=-1), tgt, in_len, tgt_len, blank=V, reduction=reduction)
+    w = torch.randn(ref.shape, generator=g) if reduction == "none" else torch.ones(())
+    (loss * w.to(DEV)).sum().backward()
+    (ref * w).sum().backward()
+    e = ((loss.cpu() - ref).abs() / ref.abs().clamp_min(1e-6)).max().item()
+    eg = ((x.grad.cpu() - xr.grad).norm() / xr.grad.norm()).item()
+    print(f"[ctc {reduction}] loss rel err {e:.2e}; dlogits rel-L2 {eg:.2e}")
+    assert e < 1e-5 and eg < 1e-4
+
+
+def test_ctc_loss_golden_reference_fixture(golden_dir):
+    """fixture produced by the unmodified reference ConvASRDecoder + CTCLoss arithmetic (tools/make_golden.py)"""
+    import os
+
+    import numpy as np
+
+    from nemo_b200.losses import B200CTCLoss
+
+    z = np.load(os.path.join(golden_dir, "ctc_head.npz"))
+    lp = torch.from_numpy(z["logp"]).to(DEV).requires_grad_(True)
+    crit = B200CTCLoss(num_classes=30, reduction="mean_batch")
+    loss = crit(log_probs=lp, targets=torch.from_numpy(z["tgt"]).to(DEV), input_lengths=torch.from_numpy(z["in_len"]).to(DEV),
+                target_lengths=torch.from_numpy(z["tgt_len"]).to(DEV))
+    assert abs(loss.item() - float(z["loss"])) < 1e-4 * abs(float(z["loss"]))
+    # gradient w.r.t. the log-probs vs torch's (the reference's) on the same log-probs
+    lr = torch.from_numpy(z["logp"]).requires_grad_(True)
+    O.ctc_loss(lr, torch.from_numpy(z["tgt"]), torch.from_numpy(z["in_len"]), torch.from_numpy(z["tgt_len"]), blank=30).backward()
+    loss.backward()
+    assert (lp.grad.cpu() - lr.grad).abs().max().item() < 1e-5
+    # infeasible utterance (target longer than the input): inf, or 0 with zero_infinity and a zero gradient
+    lp2 = torch.log_softmax(torch.randn(1, 3, 31, device=DEV), -1).requires_grad_(True)
+    t2, il2, tl2 = torch.randint(0, 30, (1, 8), device=DEV), torch.tensor([3], device=DEV), torch.tensor([8], device=DEV)
+    assert torch.isinf(B200CTCLoss(30, reduction="none")(log_probs=lp2, targets=t2, input_lengths=il2, target_lengths=tl2)).all()
+    l0 = B200CTCLoss(30, zero_infinity=True, reduction="none")(log_probs=lp2, targets=t2, input_lengths=il2, target_lengths=tl2)
+    l0.sum().backward()
+    assert l0.item() == 0.0 and lp2.grad.abs().max().item() == 0.0
