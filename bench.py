@@ -500,7 +500,7 @@ def run_ours(args):
         gemm_events.append((2.0 * M * N * K, e0, e1))
 
     def core_step(wav, wlen):
-        fg.zero()
+        opt.zero_grad()  # free after the first step: B200FusedAdamW zeroes each gradient element as it consumes it
         mel, mlen = pre(input_signal=wav, length=wlen)
         y, _ = enc(audio_signal=mel, length=mlen)
         loss = (y * proj).sum() * loss_scale

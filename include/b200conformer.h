@@ -269,10 +269,12 @@ typedef struct {
 /* One optimizer step over all tensors of `table`: AdamW with decoupled weight decay (torch.optim.AdamW arithmetic =
  * NeMo's `optim.name: adamw`, nemo/core/classes/modelPT.py:650-823; conformer_ctc_bpe.yaml:175-192) reading the flat fp32
  * gradient buffer (scaled by grad_scale), exp_avg / exp_avg_sq flat fp32 moments.  `state` [1] f64 = step count (device,
- * incremented here), `scalars` [4] f32 scratch.  The learning rate is evaluated on the device: capturable in a CUDA graph. */
-int b2c_adamw_step(const b2c_tensor_entry* table, const int32_t* blocks, int n_blocks, const float* grad_flat, float* exp_avg,
+ * incremented here), `scalars` [4] f32 scratch.  The learning rate is evaluated on the device: capturable in a CUDA graph.
+ * zero_grad != 0: every consumed gradient element is overwritten with 0 (the next step's `zero_grad()` for free: the buffer is
+ * written while it is being read, instead of a separate fill pass over it). */
+int b2c_adamw_step(const b2c_tensor_entry* table, const int32_t* blocks, int n_blocks, float* grad_flat, float* exp_avg,
                    float* exp_avg_sq, double* state, float* scalars, const b2c_adamw_hyper* hyper, float grad_scale,
-                   void* stream);
+                   int zero_grad, void* stream);
 
 typedef struct {
   const void* src;    /* fp32 [A, B, C] contiguous */

@@ -2,8 +2,9 @@
 //
 //   kernel 1 (mel_frames):   dither → pre-emphasis → length mask → centred framing (hop 160, n_fft 512) →
 //                            hann(400) window → 512-pt FFT in shared memory (two real frames packed into one
-//                            complex radix-8x8x8 Stockham transform) → |X|^2 → sparse Slaney mel → log(x + 2^-24)
-//                            → [B, n_mels, T] via a smem-staged, time-coalesced store.
+//                            complex radix-8x8x8 transform, in place in one 4 KB buffer per warp) → |X|^2 → sparse Slaney
+//                            mel → log(x + 2^-24) → [B, n_mels, T] via a smem-staged, time-coalesced store.
+//                            16 frames per CTA, 56 KB of shared memory: 4 CTAs (32 warps) per SM.
 //   kernel 2 (mel_normalize): per (b, mel) exact two-pass mean / unbiased std over frames < seq_len
 //                            (normalize_batch, features.py:59-93), normalise, zero frames >= seq_len.
 //
@@ -17,7 +18,7 @@ B2C_DEFINE_SEED_SETTER(set_seed_counter_mel)
 
 
 constexpr int kNfft = 512;
-constexpr int kFramesPerCta = 64;
+constexpr int kFramesPerCta = 16;
 constexpr int kMelWarps = 8;
 constexpr int kPad = 512 + 16;  // 512 + 512/32 padding floats
 
@@ -85,7 +86,10 @@ __global__ void mel_fb_ranges_kernel(const float* __restrict__ fb, int n_mels, i
   ranges[m] = make_int2(lo, hi);
 }
 
-__global__ void __launch_bounds__(kMelWarps * 32, 1)
+// Occupancy is what bounds this kernel (every warp runs a serial chain of shared-memory FFT stages): the per-warp FFT
+// buffer is ONE padded re/im pair used in place (stage inputs are staged through registers), the power spectra reuse it, and
+// a CTA covers only kFramesPerCta = 16 frames, so a CTA needs ~57 KB and four of them (32 warps) share an SM.
+__global__ void __launch_bounds__(kMelWarps * 32, 4)
 mel_frames_kernel(const float* __restrict__ x, const int64_t* __restrict__ length, const float* __restrict__ window,
                   const float* __restrict__ fb, const int2* __restrict__ fb_ranges, float* __restrict__ mel, int S, int T,
                   int n_mels, int win, int hop, float preemph, float dither, unsigned long long seed) {
@@ -104,8 +108,7 @@ mel_frames_kernel(const float* __restrict__ x, const int64_t* __restrict__ lengt
   float* tw_im = tw_re + kNfft;                   // [512]
   float* wsm = tw_im + kNfft;                     // [win]
   float* stage = wsm + ((win + 3) & ~3);          // [n_mels][kFramesPerCta+1]
-  float* fftbuf = stage + n_mels * (kFramesPerCta + 1);  // per warp: 2 * 2 * kPad (ping/pong re,im)
-  float* pw = fftbuf + kMelWarps * 4 * kPad;             // per warp: 2 * 260 power spectra
+  float* fftbuf = stage + n_mels * (kFramesPerCta + 1);  // per warp: 2 * kPad (re, im), used in place
 
   // twiddles e^{-2 pi i k / 512} and window
   for (int k = threadIdx.x; k < kNfft; k += blockDim.x) {
@@ -142,12 +145,8 @@ mel_frames_kernel(const float* __restrict__ x, const int64_t* __restrict__ lengt
   }
   __syncthreads();
 
-  float* bre0 = fftbuf + warp * 4 * kPad;
-  float* bim0 = bre0 + kPad;
-  float* bre1 = bim0 + kPad;
-  float* bim1 = bre1 + kPad;
-  float* pwA = pw + warp * 2 * 260;
-  float* pwB = pwA + 260;
+  float* bre = fftbuf + warp * 2 * kPad;
+  float* bim = bre + kPad;
 
   // each warp: frame pairs (2*pp, 2*pp+1) for pp = warp, warp+8, ...
   for (int pp = warp; pp * 2 < kFramesPerCta; pp += kMelWarps) {
@@ -175,44 +174,51 @@ mel_frames_kernel(const float* __restrict__ x, const int64_t* __restrict__ lengt
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const int o = padi(j * 8 + r);
-          bre0[o] = v[r].re;
-          bim0[o] = v[r].im;
+          bre[o] = v[r].re;
+          bim[o] = v[r].im;
         }
       }
       __syncwarp();
-      // ---- stage 2 (Ns = 8): buf0 → buf1
+      // ---- stage 2 (Ns = 8), in place: every lane pulls the inputs of BOTH its butterflies into registers first
+      {
+        cpx v[2][8];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int j = lane + half * 32;
+          const int k = j & 7;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int i = padi(j + r * 64);
+            cpx d = {bre[i], bim[i]};
+            const int ti = r * k * 8;  // angle = -2 pi r k / 64 = -2 pi (8 r k) / 512
+            cpx w = {tw_re[ti], tw_im[ti]};
+            v[half][r] = cmul(d, w);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int j = lane + half * 32;
+          dft8(v[half]);
+          const int j0 = (j >> 3) * 64 + (j & 7);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const int o = padi(j0 + r * 8);
+            bre[o] = v[half][r].re;
+            bim[o] = v[half][r].im;
+          }
+        }
+      }
+      __syncwarp();
+      // ---- stage 3 (Ns = 64), in place: a butterfly reads and writes the same eight slots (natural order out)
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int j = lane + half * 32;
-        const int k = j & 7;
         cpx v[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const int i = padi(j + r * 64);
-          cpx d = {bre0[i], bim0[i]};
-          const int ti = r * k * 8;  // angle = -2 pi r k / 64 = -2 pi (8 r k) / 512
-          cpx w = {tw_re[ti], tw_im[ti]};
-          v[r] = cmul(d, w);
-        }
-        dft8(v);
-        const int j0 = (j >> 3) * 64 + k;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int o = padi(j0 + r * 8);
-          bre1[o] = v[r].re;
-          bim1[o] = v[r].im;
-        }
-      }
-      __syncwarp();
-      // ---- stage 3 (Ns = 64): buf1 → buf0 (natural order)
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int j = lane + half * 32;
-        cpx v[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const int i = padi(j + r * 64);
-          cpx d = {bre1[i], bim1[i]};
+          cpx d = {bre[i], bim[i]};
           const int ti = r * j;  // angle = -2 pi r j / 512
           cpx w = {tw_re[ti], tw_im[ti]};
           v[r] = cmul(d, w);
@@ -221,22 +227,40 @@ mel_frames_kernel(const float* __restrict__ x, const int64_t* __restrict__ lengt
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           const int o = padi(j + r * 64);
-          bre0[o] = v[r].re;
-          bim0[o] = v[r].im;
+          bre[o] = v[r].re;
+          bim[o] = v[r].im;
         }
       }
       __syncwarp();
-      // ---- split the packed transform: A = (Z[k] + conj Z[-k])/2, B = (Z[k] - conj Z[-k])/(2i); power spectra
-      for (int k = lane; k < n_bins; k += 32) {
-        const int km = (kNfft - k) & (kNfft - 1);
-        const float zr = bre0[padi(k)], zi = bim0[padi(k)];
-        const float cr = bre0[padi(km)], ci = -bim0[padi(km)];
-        const float ar = 0.5f * (zr + cr), ai = 0.5f * (zi + ci);
-        const float br = 0.5f * (zi - ci), bi = -0.5f * (zr - cr);
-        // features.py:450-461: magnitude (sqrt) then pow(2.0)
-        const float ma = sqrtf(ar * ar + ai * ai), mb = sqrtf(br * br + bi * bi);
-        pwA[k] = ma * ma;
-        pwB[k] = mb * mb;
+      // ---- split the packed transform: A = (Z[k] + conj Z[-k])/2, B = (Z[k] - conj Z[-k])/(2i); the power spectra go
+      // back into the same buffer (pwA = bre[0..256], pwB = bim[0..256], unpadded), so read everything first
+      {
+        float pa[9], pb[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+          const int k = lane + q * 32;
+          pa[q] = pb[q] = 0.f;
+          if (k < n_bins) {
+            const int km = (kNfft - k) & (kNfft - 1);
+            const float zr = bre[padi(k)], zi = bim[padi(k)];
+            const float cr = bre[padi(km)], ci = -bim[padi(km)];
+            const float ar = 0.5f * (zr + cr), ai = 0.5f * (zi + ci);
+            const float br = 0.5f * (zi - ci), bi = -0.5f * (zr - cr);
+            // features.py:450-461: magnitude (sqrt) then pow(2.0)
+            const float ma = sqrtf(ar * ar + ai * ai), mb = sqrtf(br * br + bi * bi);
+            pa[q] = ma * ma;
+            pb[q] = mb * mb;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+          const int k = lane + q * 32;
+          if (k < n_bins) {
+            bre[k] = pa[q];
+            bim[k] = pb[q];
+          }
+        }
       }
       __syncwarp();
       // ---- sparse mel projection + log (features.py:469-475)
@@ -246,8 +270,8 @@ mel_frames_kernel(const float* __restrict__ x, const int64_t* __restrict__ lengt
         float sa = 0.f, sb = 0.f;
         for (int k = rg.x; k < rg.y; ++k) {
           const float w = __ldg(f + k);
-          sa = fmaf(w, pwA[k], sa);
-          sb = fmaf(w, pwB[k], sb);
+          sa = fmaf(w, bre[k], sa);
+          sb = fmaf(w, bim[k], sb);
         }
         stage[m * (kFramesPerCta + 1) + fa] = logf(sa + 5.9604644775390625e-08f);
         stage[m * (kFramesPerCta + 1) + fbf] = logf(sb + 5.9604644775390625e-08f);
@@ -345,11 +369,12 @@ extern "C" int b2c_mel_frontend(const float* x, const int64_t* length, const flo
   if (rc) return rc;
   const int ylen = (kFramesPerCta - 1) * hop + win;
   const size_t smem = sizeof(float) * (size_t)(((ylen + 3) & ~3) + 2 * kNfft + ((win + 3) & ~3) +
-                                               n_mels * (kFramesPerCta + 1) + kMelWarps * 4 * kPad + kMelWarps * 2 * 260);
+                                               n_mels * (kFramesPerCta + 1) + kMelWarps * 2 * kPad);
   B2C_REQUIRE(smem <= 227 * 1024, "mel_frontend: smem %zu too large", smem);
   static size_t smem_set = 0;
   if (smem > smem_set) {
     B2C_CUDA(cudaFuncSetAttribute(mel_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2C_CUDA(cudaFuncSetAttribute(mel_frames_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     smem_set = smem;
   }
   dim3 grid((T + kFramesPerCta - 1) / kFramesPerCta, B);

@@ -66,15 +66,15 @@ __device__ __forceinline__ void adamw_one(float& p, float& m, float& v, float g,
 }
 
 __global__ void __launch_bounds__(256)
-adamw_apply_kernel(const b2c_tensor_entry* __restrict__ table, const int2* __restrict__ blocks, const float* __restrict__ grad,
+adamw_apply_kernel(const b2c_tensor_entry* __restrict__ table, const int2* __restrict__ blocks, float* __restrict__ grad,
                    float* __restrict__ m_, float* __restrict__ v_, const float* __restrict__ scal, float beta1, float beta2,
-                   float eps, float grad_scale) {
+                   float eps, float grad_scale, int zero_grad) {
   const int2 bk = blocks[blockIdx.x];
   const b2c_tensor_entry e = table[bk.x];
   const long long i0 = (long long)bk.y * kChunk;
   const int n = (int)min((long long)kChunk, e.numel - i0);
   float* p = reinterpret_cast<float*>(e.ptr) + i0;
-  const float* g = grad + e.offset + i0;
+  float* g = grad + e.offset + i0;
   float* m = m_ + e.offset + i0;
   float* v = v_ + e.offset + i0;
   const float step_size = scal[1], inv_sqrt_bc2 = scal[2], decay = e.flags & 1 ? 1.f : scal[3];
@@ -90,12 +90,17 @@ adamw_apply_kernel(const b2c_tensor_entry* __restrict__ table, const int2* __res
       *reinterpret_cast<float4*>(p + i) = pp;
       *reinterpret_cast<float4*>(m + i) = mm;
       *reinterpret_cast<float4*>(v + i) = vv;
+      if (zero_grad) *reinterpret_cast<float4*>(g + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int i = (n & ~3) + threadIdx.x; i < n; i += 256)
+    for (int i = (n & ~3) + threadIdx.x; i < n; i += 256) {
       adamw_one(p[i], m[i], v[i], g[i] * grad_scale, beta1, beta2, eps, step_size, inv_sqrt_bc2, decay);
+      if (zero_grad) g[i] = 0.f;
+    }
   } else {
-    for (int i = threadIdx.x; i < n; i += 256)
+    for (int i = threadIdx.x; i < n; i += 256) {
       adamw_one(p[i], m[i], v[i], g[i] * grad_scale, beta1, beta2, eps, step_size, inv_sqrt_bc2, decay);
+      if (zero_grad) g[i] = 0.f;
+    }
   }
 }
 
@@ -153,9 +158,9 @@ extern "C" int b2c_set_seed_counter(const unsigned long long* counter) {
   return B2C_OK;
 }
 
-extern "C" int b2c_adamw_step(const b2c_tensor_entry* table, const int32_t* blocks, int n_blocks, const float* grad_flat,
+extern "C" int b2c_adamw_step(const b2c_tensor_entry* table, const int32_t* blocks, int n_blocks, float* grad_flat,
                               float* exp_avg, float* exp_avg_sq, double* state, float* scalars, const b2c_adamw_hyper* hyper,
-                              float grad_scale, void* stream) {
+                              float grad_scale, int zero_grad, void* stream) {
   B2C_REQUIRE(table && blocks && grad_flat && exp_avg && exp_avg_sq && state && scalars && hyper, "adamw_step: null argument");
   B2C_REQUIRE(n_blocks > 0, "adamw_step: empty block table");
   B2C_REQUIRE(hyper->beta1 >= 0.f && hyper->beta1 < 1.f && hyper->beta2 >= 0.f && hyper->beta2 < 1.f && hyper->eps > 0.f,
@@ -164,7 +169,7 @@ extern "C" int b2c_adamw_step(const b2c_tensor_entry* table, const int32_t* bloc
   B2C_LAUNCH_CHECK();
   adamw_apply_kernel<<<n_blocks, 256, 0, (cudaStream_t)stream>>>(table, reinterpret_cast<const int2*>(blocks), grad_flat, exp_avg,
                                                                  exp_avg_sq, scalars, hyper->beta1, hyper->beta2, hyper->eps,
-                                                                 grad_scale);
+                                                                 grad_scale, zero_grad);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
 }

@@ -148,13 +148,19 @@ subsample_conv1_bwd_kernel(const float* __restrict__ mel, const bf16* __restrict
 }
 
 // depthwise Conv2d(C, 3x3, s2, p1, groups=C) on channels-last [B,T1,F1,C] → [B,T2,F2,C], + bias, output masked t2<len
-// (input is already time-masked by its producer).  thread = channel pair; CTA = (b, t2) row.
-__global__ void __launch_bounds__(256)
+// (input is already time-masked by its producer).  thread = (channel pair, slice of the f axis); CTA = (b, t2) row.
+// With C = 256 (FastConformer) there are only 128 channel pairs: the 512 threads of a CTA split the f positions four ways
+// (`fpart`, stride `fs`) so that no thread idles and four times as many loads are in flight per row.
+constexpr int kDwThreads = 512;
+__global__ void __launch_bounds__(kDwThreads)
 dwconv3x3s2_fwd_kernel(const bf16* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                        const int32_t* __restrict__ len_out, bf16* __restrict__ out, int T1, int F1, int C, int T2, int F2) {
   const int t2 = blockIdx.x, b = blockIdx.y;
   const bool valid = len_out ? (t2 < len_out[b]) : true;
-  for (int cp = threadIdx.x; cp * 2 < C; cp += blockDim.x) {
+  const int CP = C >> 1, fs = max(1, (int)blockDim.x / CP);
+  const int fpart = (CP >= (int)blockDim.x) ? 0 : (int)threadIdx.x / CP;
+  if (fpart >= fs) return;
+  for (int cp = (CP >= (int)blockDim.x) ? (int)threadIdx.x : (int)threadIdx.x % CP; cp < CP; cp += (CP >= (int)blockDim.x) ? (int)blockDim.x : CP) {
     const int c = cp * 2;
     float w0[9], w1[9];
 #pragma unroll
@@ -163,7 +169,7 @@ dwconv3x3s2_fwd_kernel(const bf16* __restrict__ in, const float* __restrict__ w,
       w1[j] = bf16_round(w[(size_t)(c + 1) * 9 + j]);
     }
     const float b0 = bias[c], b1 = bias[c + 1];
-    for (int f2 = 0; f2 < F2; ++f2) {
+    for (int f2 = fpart; f2 < F2; f2 += fs) {
       float a0 = 0.f, a1 = 0.f;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
@@ -186,13 +192,16 @@ dwconv3x3s2_fwd_kernel(const bf16* __restrict__ in, const float* __restrict__ w,
 
 // depthwise 3x3 s2 backward, data: dx[b,t1,f1,c] = (x[b,t1,f1,c] > 0) * sum_{kh,kw} dy[b,(t1+1-kh)/2,(f1+1-kw)/2,c] * w[c,kh,kw]
 // (dy rows t2 >= len_out count as zero: the forward masks the depthwise output before the pointwise conv)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kDwThreads)
 dwconv3x3s2_bwd_data_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ w,
                             const int32_t* __restrict__ len_out, bf16* __restrict__ dx, int T1, int F1, int C, int T2,
                             int F2) {
   const int t1 = blockIdx.x, b = blockIdx.y;
   const int lout = len_out ? len_out[b] : T2;
-  for (int cp = threadIdx.x; cp * 2 < C; cp += blockDim.x) {
+  const int CP = C >> 1, fs = max(1, (int)blockDim.x / CP);
+  const int fpart = (CP >= (int)blockDim.x) ? 0 : (int)threadIdx.x / CP;
+  if (fpart >= fs) return;
+  for (int cp = (CP >= (int)blockDim.x) ? (int)threadIdx.x : (int)threadIdx.x % CP; cp < CP; cp += (CP >= (int)blockDim.x) ? (int)blockDim.x : CP) {
     const int c = cp * 2;
     float w0[9], w1[9];
 #pragma unroll
@@ -200,7 +209,7 @@ dwconv3x3s2_bwd_data_kernel(const bf16* __restrict__ dy, const bf16* __restrict_
       w0[j] = bf16_round(w[(size_t)c * 9 + j]);
       w1[j] = bf16_round(w[(size_t)(c + 1) * 9 + j]);
     }
-    for (int f1 = 0; f1 < F1; ++f1) {
+    for (int f1 = fpart; f1 < F1; f1 += fs) {
       float a0 = 0.f, a1 = 0.f;
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh) {
@@ -227,20 +236,23 @@ dwconv3x3s2_bwd_data_kernel(const bf16* __restrict__ dy, const bf16* __restrict_
 }
 
 // weight / bias gradients of the depthwise 3x3 s2 conv: dw[c,kh,kw] += sum dy[b,t2,f2,c] * x[b,2t2+kh-1,2f2+kw-1,c]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kDwThreads)
 dwconv3x3s2_bwd_weight_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const int32_t* __restrict__ len_out,
                               float* __restrict__ dw, float* __restrict__ dbias, int T1, int F1, int C, int T2, int F2,
                               int rows_per_cta) {
   const int b = blockIdx.y;
   const int lout = len_out ? min(len_out[b], T2) : T2;
   const int t2_0 = blockIdx.x * rows_per_cta, t2_1 = min(lout, t2_0 + rows_per_cta);
-  for (int cp = threadIdx.x; cp * 2 < C; cp += blockDim.x) {
+  const int CP = C >> 1, fs = max(1, (int)blockDim.x / CP);
+  const int fpart = (CP >= (int)blockDim.x) ? 0 : (int)threadIdx.x / CP;
+  if (fpart >= fs) return;
+  for (int cp = (CP >= (int)blockDim.x) ? (int)threadIdx.x : (int)threadIdx.x % CP; cp < CP; cp += (CP >= (int)blockDim.x) ? (int)blockDim.x : CP) {
     const int c = cp * 2;
     float g0[9], g1[9], d0 = 0.f, d1 = 0.f;
 #pragma unroll
     for (int j = 0; j < 9; ++j) g0[j] = g1[j] = 0.f;
     for (int t2 = t2_0; t2 < t2_1; ++t2) {
-      for (int f2 = 0; f2 < F2; ++f2) {
+      for (int f2 = fpart; f2 < F2; f2 += fs) {
         const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(dy + (((size_t)b * T2 + t2) * F2 + f2) * C + c));
         d0 += g.x; d1 += g.y;
 #pragma unroll
@@ -313,7 +325,7 @@ extern "C" int b2c_dwconv3x3s2_fwd(const void* in_bf16, const float* w, const fl
                                    void* out_bf16, int B, int T1, int F1, int C, void* stream) {
   B2C_REQUIRE(C % 2 == 0 && B > 0 && T1 > 0 && F1 > 0, "dwconv3x3s2_fwd: bad shape");
   const int T2 = (T1 + 2 - 3) / 2 + 1, F2 = (F1 + 2 - 3) / 2 + 1;
-  dwconv3x3s2_fwd_kernel<<<dim3(T2, B), 256, 0, (cudaStream_t)stream>>>(
+  dwconv3x3s2_fwd_kernel<<<dim3(T2, B), kDwThreads, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const bf16*>(in_bf16), w, bias, len_out, reinterpret_cast<bf16*>(out_bf16), T1, F1, C, T2, F2);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
@@ -323,12 +335,12 @@ extern "C" int b2c_dwconv3x3s2_bwd(const void* dy_bf16, const void* x_bf16, cons
                                    void* dx_bf16, float* dw, float* dbias, int B, int T1, int F1, int C, void* stream) {
   B2C_REQUIRE(C % 2 == 0 && B > 0 && T1 > 0 && F1 > 0, "dwconv3x3s2_bwd: bad shape");
   const int T2 = (T1 + 2 - 3) / 2 + 1, F2 = (F1 + 2 - 3) / 2 + 1;
-  dwconv3x3s2_bwd_data_kernel<<<dim3(T1, B), 256, 0, (cudaStream_t)stream>>>(
+  dwconv3x3s2_bwd_data_kernel<<<dim3(T1, B), kDwThreads, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const bf16*>(dy_bf16), reinterpret_cast<const bf16*>(x_bf16), w, len_out,
       reinterpret_cast<bf16*>(dx_bf16), T1, F1, C, T2, F2);
   B2C_LAUNCH_CHECK();
   const int rows = 8;
-  dwconv3x3s2_bwd_weight_kernel<<<dim3((T2 + rows - 1) / rows, B), 256, 0, (cudaStream_t)stream>>>(
+  dwconv3x3s2_bwd_weight_kernel<<<dim3((T2 + rows - 1) / rows, B), kDwThreads, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const bf16*>(dy_bf16), reinterpret_cast<const bf16*>(x_bf16), len_out, dw, dbias, T1, F1, C, T2, F2,
       rows);
   B2C_LAUNCH_CHECK();

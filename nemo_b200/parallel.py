@@ -48,10 +48,16 @@ def grad_layout(named_params):
 class FlatGradients:
     """Owns the flat gradient buffer of a module and the layer-wise overlapped all-reduce."""
 
-    def __init__(self, module: torch.nn.Module, process_group=None, grad_dtype=torch.float32, defer: bool = False):
+    def __init__(self, module: torch.nn.Module, process_group=None, grad_dtype=torch.float32, defer: bool = False,
+                 bucket_bytes: int = 96 << 20):
         self.module = module
         self.group = process_group
         self.defer = defer
+        # finished layer slices are coalesced into buckets of at least this many bytes before their all-reduce is launched:
+        # a handful of large NCCL calls per step instead of one per layer (each call's channel CTAs share the SMs with the
+        # backward GEMMs that are still running; fewer, larger calls cost less of their throughput — profiles/r01_scaling.md)
+        self.bucket_bytes = int(bucket_bytes)
+        self._pending = None  # [lo, hi) of finished-but-not-yet-reduced gradients (contiguous: backward walks the layers in order)
         params = grad_layout((n, p) for n, p in module.named_parameters() if p.requires_grad)
         self.names = [n for n, _ in params]
         self.sizes = [p.numel() for _, p in params]
@@ -73,6 +79,7 @@ class FlatGradients:
         the default set_to_none=True (what Lightning / NeMo call) detaches them — and refuse a second backward into a
         buffer that has already been all-reduced (that would reduce the first micro-batch twice).  Use `zero()` instead
         of `zero_grad()`; for gradient accumulation construct with `defer=True` (one all-reduce in `finish()`)."""
+        self._zeroed = False
         if self._reduced and self._world() > 1:
             raise RuntimeError("FlatGradients: backward into an already all-reduced buffer; call zero() between steps "
                                "(gradient accumulation: FlatGradients(..., defer=True))")
@@ -111,9 +118,20 @@ class FlatGradients:
 
     def ready(self, lo: int, hi: int):
         """Gradients in flat[lo:hi] are final (their kernels are enqueued on the current stream)."""
-        if self.defer:
+        if self.defer or self._world() <= 1 or hi <= lo:
             return
-        if self._world() > 1 and hi > lo:
+        if self._pending is not None and (lo == self._pending[1] or hi == self._pending[0]):
+            self._pending = [min(lo, self._pending[0]), max(hi, self._pending[1])]
+        else:
+            self._flush()
+            self._pending = [lo, hi]
+        if (self._pending[1] - self._pending[0]) * self.flat.element_size() >= self.bucket_bytes:
+            self._flush()
+
+    def _flush(self):
+        if self._pending is not None:
+            lo, hi = self._pending
+            self._pending = None
             self._reduced = True
             self._handles.append(dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
@@ -123,13 +141,23 @@ class FlatGradients:
 
     def zero(self):
         self.flat.zero_()
+        self.mark_zeroed()
+
+    def mark_zeroed(self):
+        """the flat buffer is all zeros again (after zero(), or after an optimizer step that zeroed what it consumed)"""
         self._reduced = False
+        self._pending = None
+        self._zeroed = True
+
+    def is_zeroed(self) -> bool:
+        return bool(self.__dict__.get("_zeroed", False))
 
     def finish(self):
         """Wait for the outstanding all-reduces (the current stream waits; no host sync for NCCL)."""
         if self.defer and self._world() > 1:
             self._reduced = True
             self._handles.append(dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self._flush()
         for h in self._handles:
             h.wait()
         self._handles.clear()

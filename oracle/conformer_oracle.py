@@ -91,13 +91,17 @@ def mel_frontend(
     fb: Optional[torch.Tensor] = None,
     window: Optional[torch.Tensor] = None,
     return_prenorm=False,
+    dtype=torch.float32,
 ):
     """FilterbankFeatures.forward in eval mode (no dither), features.py:423-502.
-    x [B,S] f32, length [B] int → (mel [B,n_mels,T] f32, seq_len [B] i64)."""
-    x = x.to(torch.float32)
+    x [B,S] f32, length [B] int → (mel [B,n_mels,T] f32, seq_len [B] i64).
+    dtype=torch.float64 evaluates the same formulas in double precision: the "truth" against which the fp32 rounding noise
+    of torch.stft itself (and of the CUDA FFT) is measured in the tests."""
+    x = x.to(dtype)
     seq_len = mel_seq_len(length, n_fft, hop)
     if window is None:
         window = torch.hann_window(win_length, periodic=False, dtype=torch.float32)  # features.py:326
+    window = window.to(dtype)
     if fb is None:
         fb = torch.from_numpy(slaney_mel_filterbank(sample_rate, n_fft, n_mels))
     fb = fb.reshape(-1, fb.shape[-1]).to(x.device)

@@ -141,6 +141,7 @@ def test_mel_frontend_vs_oracle(B, secs, ragged):
     if ragged:
         length[-1] = min(799, x.shape[1])
     ref, ref_len, ref_raw = O.mel_frontend(x, length, return_prenorm=True)
+    _, _, truth_raw = O.mel_frontend(x, length, return_prenorm=True, dtype=torch.float64)  # same formulas in double
     pre = B200MelPreprocessor(sample_rate=16000, window_size=0.025, window_stride=0.01, features=80, n_fft=512,
                               dither=1e-5, pad_to=0).to(DEV).eval()
     mel, mlen = pre(input_signal=x.to(DEV), length=length.to(DEV))
@@ -149,9 +150,17 @@ def test_mel_frontend_vs_oracle(B, secs, ragged):
     raw, _ = pre.featurizer.forward_raw(x.to(DEV), length.to(DEV))
     valid = (torch.arange(ref.shape[-1])[None, :] < ref_len[:, None])[:, None, :]
     err_raw = ((raw.cpu() - ref_raw) * valid).abs().max().item()
+    err_truth = ((raw.cpu().double() - truth_raw) * valid).abs().max().item()
+    ref_truth = ((ref_raw.double() - truth_raw) * valid).abs().max().item()
     err = (mel.cpu() - ref).abs().max().item()
-    print(f"[mel B={B} {secs}s] log-mel abs err {err_raw:.2e}; normalised abs err {err:.2e}")
-    assert err_raw < 1e-3  # fp32 FFT vs torch.stft: log of sums of ~1e-6 powers
+    print(f"[mel B={B} {secs}s] log-mel max-abs err: cuda vs torch.stft(fp32) {err_raw:.2e}; vs float64 truth: cuda {err_truth:.2e} | "
+          f"torch.stft(fp32) {ref_truth:.2e}; normalised abs err {err:.2e}")
+    # SURVEY §8c policy: <= 1e-4 on the pre-normalisation log-mel.  Both fp32 pipelines sit ~1e-4 from the float64 truth on the
+    # worst bin (log of a sum of ~1e-6 powers amplifies the FFT's 1e-7 rounding), so the gate is on the distance to the TRUTH:
+    # the CUDA front-end may not be further from it than the reference's own fp32 torch.stft path (x1.5), nor than 1e-4 when
+    # the reference is that accurate itself.
+    assert err_truth <= max(1e-4, 1.5 * ref_truth)
+    assert err_raw <= max(2e-4, 2.5 * ref_truth)
     assert err < 5e-3
     assert torch.equal(mel.cpu()[~valid.expand_as(ref)], torch.zeros_like(ref)[~valid.expand_as(ref)])
 
