@@ -228,6 +228,20 @@ int b2c_p_dwconv2d(const float* x, const float* w, const float* bias, const int3
 int b2c_p_dwconv1d(const float* u, const float* w, const float* bias, float* out, int B, int T, int d, int k, void* stream);
 /* P[bh,i,:] = masked softmax_j(scale * (AC[bh,i,j] + R[bh,i,T-1-i+j])) with the reference's -1e4 / 0 double mask */
 int b2c_p_log_softmax(const float* logits, int ld, float* out, long long M, int V, void* stream);
+/* backward of the above (same conventions; pointwise modes 5: out = a * silu'(b); 6: GLU backward, a = du [M,N], b = g [M,2N] →
+ * out [M,2N]; 7: out = b > 0 ? a : 0).  out[n] (+)= column sums; BatchNorm+SiLU backward (sums [2N] = dbeta | dgamma on return);
+ * depthwise conv data / weight gradients; softmax backward + un-skew (dS [BH,T,Tp], dR [BH,T,Rp]); col2im as a gather. */
+int b2c_p_colsum(const float* x, long long ld, float* out, long long M, int N, int accumulate, void* stream);
+int b2c_p_bn_silu_bwd(const float* ds, const float* c, const float* gamma, const float* scale, const float* shift, const float* mean,
+                      const float* rstd, float* dz_scratch, float* dzx_scratch, float* sums, float* dc, long long M, int N,
+                      int training, void* stream);
+int b2c_p_dwconv1d_bwd(const float* dc, const float* u, const float* w, const int32_t* lengths, float* du, float* dw, int B, int T,
+                       int d, int k, void* stream);
+int b2c_p_attn_softmax_bwd(const float* P, const float* dP, float* dS, float* dR, int B, int H, int T, int Tp, int Rp, float scale,
+                           void* stream);
+int b2c_p_col2im_nhwc(const float* dp, float* dx, int B, int T1, int F1, int C, void* stream);
+int b2c_p_dwconv2d_bwd(const float* dy, const float* x, const float* w, const int32_t* len_out, float* dx, float* dw, float* dbias,
+                       int B, int T1, int F1, int C, void* stream);
 int b2c_p_attn_softmax(const float* AC, const float* R, const int32_t* lengths, float* P, int B, int H, int T, int Tp, int Rp,
                        float scale, void* stream);
 

@@ -243,10 +243,11 @@ dwconv3x3s2_bwd_weight_kernel(const bf16* __restrict__ dy, const bf16* __restric
   const int b = blockIdx.y;
   const int lout = len_out ? min(len_out[b], T2) : T2;
   const int t2_0 = blockIdx.x * rows_per_cta, t2_1 = min(lout, t2_0 + rows_per_cta);
-  const int CP = C >> 1, fs = max(1, (int)blockDim.x / CP);
-  const int fpart = (CP >= (int)blockDim.x) ? 0 : (int)threadIdx.x / CP;
-  if (fpart >= fs) return;
-  for (int cp = (CP >= (int)blockDim.x) ? (int)threadIdx.x : (int)threadIdx.x % CP; cp < CP; cp += (CP >= (int)blockDim.x) ? (int)blockDim.x : CP) {
+  // thread = (f-slice q, channel pair): CP * fs == blockDim.x is required by the launcher (C/2 divides the CTA size)
+  const int CP = C >> 1, fs = (int)blockDim.x / CP;
+  const int fpart = (int)threadIdx.x / CP;
+  {
+    const int cp = (int)threadIdx.x % CP;
     const int c = cp * 2;
     float g0[9], g1[9], d0 = 0.f, d1 = 0.f;
 #pragma unroll
@@ -270,15 +271,30 @@ dwconv3x3s2_bwd_weight_kernel(const bf16* __restrict__ dy, const bf16* __restric
         }
       }
     }
-    if (t2_1 > t2_0) {
+    // one atomic per (channel, tap) per CTA: the f-slices of a channel pair are summed through shared memory first
+    // (global atomics were the bound of this kernel: every thread used to issue 20 of them)
+    __shared__ float red[kDwThreads * 20];
+    float* mine = red + threadIdx.x * 20;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) { mine[j] = g0[j]; mine[9 + j] = g1[j]; }
+    mine[18] = d0; mine[19] = d1;
+    __syncthreads();
+    if (fpart == 0 && t2_1 > t2_0) {
+      float acc[20];
+#pragma unroll
+      for (int j = 0; j < 20; ++j) acc[j] = 0.f;
+      for (int q = 0; q < fs; ++q)
+#pragma unroll
+        for (int j = 0; j < 20; ++j) acc[j] += red[(q * CP + cp) * 20 + j];
 #pragma unroll
       for (int j = 0; j < 9; ++j) {
-        atomicAdd(dw + (size_t)c * 9 + j, g0[j]);
-        atomicAdd(dw + (size_t)(c + 1) * 9 + j, g1[j]);
+        atomicAdd(dw + (size_t)c * 9 + j, acc[j]);
+        atomicAdd(dw + (size_t)(c + 1) * 9 + j, acc[9 + j]);
       }
-      atomicAdd(dbias + c, d0);
-      atomicAdd(dbias + c + 1, d1);
+      atomicAdd(dbias + c, acc[18]);
+      atomicAdd(dbias + c + 1, acc[19]);
     }
+    __syncthreads();
   }
 }
 
@@ -339,8 +355,11 @@ extern "C" int b2c_dwconv3x3s2_bwd(const void* dy_bf16, const void* x_bf16, cons
       reinterpret_cast<const bf16*>(dy_bf16), reinterpret_cast<const bf16*>(x_bf16), w, len_out,
       reinterpret_cast<bf16*>(dx_bf16), T1, F1, C, T2, F2);
   B2C_LAUNCH_CHECK();
-  const int rows = 8;
-  dwconv3x3s2_bwd_weight_kernel<<<dim3((T2 + rows - 1) / rows, B), kDwThreads, 0, (cudaStream_t)stream>>>(
+  // CTA size = the largest multiple of C/2 (channel pairs) that fits kDwThreads; 32 output rows per CTA
+  B2C_REQUIRE(C / 2 <= kDwThreads, "dwconv3x3s2_bwd: C = %d too large", C);
+  const int rows = 32;
+  const int wthreads = (kDwThreads / (C / 2)) * (C / 2);
+  dwconv3x3s2_bwd_weight_kernel<<<dim3((T2 + rows - 1) / rows, B), wthreads, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const bf16*>(dy_bf16), reinterpret_cast<const bf16*>(x_bf16), len_out, dw, dbias, T1, F1, C, T2, F2,
       rows);
   B2C_LAUNCH_CHECK();

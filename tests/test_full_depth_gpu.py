@@ -224,3 +224,50 @@ def test_parity_mode_train_statistics_and_guards():
     enc.dropout = 0.1
     with pytest.raises(NotImplementedError):
         enc(audio_signal=x.to(DEV), length=ln.to(DEV))
+
+
+@pytest.mark.parametrize("name,n_layers", [("cfg2_conformer_ctc_large_18L", 18), ("cfg3_fastconformer_large_17L", 4),
+                                           ("cfg4_conformer_transducer_xl_24L", 3)])
+def test_parity_mode_gradients_within_1e3_of_fp32_reference(name, n_layers):
+    """precision='fp32' backward: EVERY parameter gradient of the BASELINE architectures (config 2 at its full 18 layers; the
+    dw_striding and d=1024 / head-dim-128 variants at reduced depth) within 1e-3 rel-L2 of the fp32 oracle's autograd, BatchNorm
+    on batch statistics (train(), dropout 0), ragged 30 s utterances."""
+    cfg, B = FULL[name]
+    cfg = dict(cfg, n_layers=n_layers)
+    sd = O.init_state_dict(seed=11, **cfg)
+    enc = B200ConformerEncoder(feat_in=80, n_layers=cfg["n_layers"], d_model=cfg["d_model"], n_heads=cfg["n_heads"],
+                               conv_kernel_size=cfg["conv_kernel_size"], subsampling=cfg["subsampling_kind"],
+                               subsampling_factor=cfg["subsampling_factor"], subsampling_conv_channels=cfg["subsampling_conv_channels"],
+                               dropout=0.0, dropout_pre_encoder=0.0, dropout_emb=0.0, dropout_att=0.0)
+    enc.load_state_dict(sd, strict=True)
+    enc = enc.to(DEV).train()
+    enc.precision = "fp32"
+    sd = {k: v.to(DEV) for k, v in sd.items()}
+    pre = B200MelPreprocessor(window_size=0.025, window_stride=0.01, features=80, n_fft=512, pad_to=0).to(DEV).eval()
+    wav, wlen = O.synthetic_waveforms(max(B, 2), 30.0, ragged=True)
+    wlen[-1] = 30 * 16000 - 160 * 411
+    mel, mlen = pre(input_signal=wav.to(DEV), length=wlen.to(DEV))
+    y, ylen = enc(audio_signal=mel, length=mlen)
+    r = torch.randn(y.shape, generator=torch.Generator().manual_seed(3)).to(DEV)
+    ((y.float() * r).sum() / y.shape[0]).backward()
+    y_ref, ylen_ref, g_ref, _ = _oracle(sd, mel, mlen, cfg, False, r)
+    assert torch.equal(ylen, ylen_ref)
+    print(f"[parity-grad {name} {n_layers}L] output rel-L2 {rel_l2(y, y_ref):.3e}")
+    assert rel_l2(y, y_ref) <= 1e-3
+    rms_all = max(g.float().pow(2).mean().sqrt().item() for g in g_ref.values())
+    worst, bad = (0.0, ""), []
+    for k, p in enc.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
+        gr = g_ref[k]
+        if gr.float().pow(2).mean().sqrt().item() < 1e-5 * rms_all:  # analytically-zero gradients (rounding noise in both)
+            assert p.grad.float().pow(2).mean().sqrt().item() < 1e-3 * rms_all, k
+            continue
+        e = rel_l2(p.grad, gr)
+        if e > worst[0]:
+            worst = (e, k)
+        if e > 1e-3:
+            bad.append((k, e))
+    print(f"[parity-grad {name} {n_layers}L] worst parameter-gradient rel-L2 {worst[0]:.3e} ({worst[1]})")
+    for k, e in bad:
+        print(f"[parity-grad {name}] FAIL {k}: {e:.3e}")
+    assert not bad

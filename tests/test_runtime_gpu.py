@@ -122,7 +122,7 @@ def test_seed_counter_changes_masks_and_captured_step_equals_eager():
     """(1) the device counter alone (same by-value seed) changes the dropout masks; (2) a captured training step replayed k
     times lands on the same weights as k eager steps with the same counter values; (3) replays draw fresh masks."""
     ctr = seed_counter()
-    x = torch.randn(2, 80, 160, device=DEV)
+    x = torch.randn(2, 80, 160, generator=torch.Generator().manual_seed(12)).to(DEV)
     ln = torch.tensor([160, 111], device=DEV)
 
     def make():
@@ -143,7 +143,7 @@ def test_seed_counter_changes_masks_and_captured_step_equals_eager():
         y2, _ = enc(audio_signal=x, length=ln)
     assert torch.equal(y1, y1b) and not torch.equal(y1, y2)
 
-    r = torch.randn(y1.shape, device=DEV)
+    r = torch.randn(y1.shape, generator=torch.Generator().manual_seed(13)).to(DEV)
     # eager: 3 steps at counter values 201, 202, 203
     enc_e, fg_e, opt_e = make()
     losses_e = []
@@ -168,7 +168,9 @@ def test_seed_counter_changes_masks_and_captured_step_equals_eager():
     for (n, p), (_, q) in zip(enc_e.named_parameters(), enc_g.named_parameters()):
         worst = max(worst, ((p - q).norm() / p.norm().clamp_min(1e-12)).item())
     print("captured vs eager weights after 3 steps: worst rel-L2", worst)
-    assert worst < 1e-3  # split-K atomics reorder fp32 sums; everything else is identical
+    # split-K atomics reorder fp32 sums (a last-bit difference that can flip a bf16 rounding downstream); everything else
+    # is identical.  Observed 7e-6 ... 1e-3 depending on the data; a wrong mask / stale weight would be O(1).
+    assert worst < 5e-3
     ctr.zero_()
 
 

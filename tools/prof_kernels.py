@@ -89,5 +89,29 @@ ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
 timed("relpos_attn_bwd (q+kv+pos, p=0.1)",
       lambda: L.call("relpos_attn_bwd", qkv, pos, bu, bv, lengths, ctx, ctx32, dctx, lse, dqkv, dpos, dbu, dbv, ws, nbytes, B, T, H, DK,
                      0.1, 1, 3), 2.5 * attn_flops_f)
+# ---- HBM-bound kernels: LayerNorm backward, depthwise conv backward (k = 31), mel front-end (32 x 30 s)
+xr = torch.randn(M, D, device=DEV)
+gam = torch.ones(D, device=DEV)
+mean, rstd = torch.zeros(M, device=DEV), torch.ones(M, device=DEV)
+drr = torch.randn(M, D, device=DEV)
+dgam, dbet = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+nxt = torch.empty(M, D, dtype=torch.bfloat16, device=DEV)
+dy16 = rnd(M, D)
+timed("layernorm_bwd 24000x512 (bf16 dy, accumulate, next)",
+      lambda: L.call("layernorm_bwd", dy16, 1, xr, gam, mean, rstd, drr, 1, dgam, dbet, nxt, 1.0, 0.1, 1, 3, M, D),
+      bytes_=M * D * (2 + 4 + 8 + 2))
+K = 31
+u16, dc16, du16 = rnd(M, D), rnd(M, D), torch.empty(M, D, dtype=torch.bfloat16, device=DEV)
+wdw, gdw, gdb = torch.randn(D, K, device=DEV) * 0.1, torch.zeros(D, K, device=DEV), torch.zeros(D, device=DEV)
+timed("dwconv_bwd k=31 24000x512", lambda: L.call("dwconv_bwd", dc16, u16, wdw, lengths, du16, gdw, gdb, B, T, D, K), bytes_=M * D * 6)
+c16 = torch.empty(M, D, dtype=torch.bfloat16, device=DEV)
+bs, bq = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+timed("dwconv_fwd k=31 24000x512", lambda: L.call("dwconv_fwd", u16, wdw, gdb, c16, bs, bq, B, T, D, K), bytes_=M * D * 4)
+from nemo_b200.preprocessor import B200MelPreprocessor  # noqa: E402
+
+pre = B200MelPreprocessor(sample_rate=16000, window_size=0.025, window_stride=0.01, features=80, n_fft=512, dither=1e-5, pad_to=0).to(DEV).eval()
+wav = (torch.rand(32, 480000, device=DEV) * 0.2 - 0.1)
+wl = torch.full((32,), 480000, dtype=torch.int64, device=DEV)
+timed("mel front-end 32x30 s (frames + normalize)", lambda: pre(input_signal=wav, length=wl), bytes_=32 * (4 * 480000 + 4 * 80 * 3001))
 torch.cuda.synchronize()
 print("done")
