@@ -383,6 +383,11 @@ class _Pass:
         _pw(P_AXPY, None, dr, dxo, M, d, alpha=enc.xscale or 1.0)
         gwo = Z(d, F2 * C)
         dxl = _linear_bwd(dxo, S["xls"], S["wos"], M, d, F2 * C, gwo, G["pre_encode.out.bias"])
+        dbg = enc.__dict__.get("_debug_parity")  # tests / tools/debug: intermediates of the subsampling stack
+        if dbg is not None:
+            dbg["dr"], dbg["dxl"] = dr.clone(), dxl.clone()
+            # the ReLU outputs in forward order ([B,T,F,C]): their signs are the gates the backward used
+            dbg["relu_out"] = [S["x1"]] + ([st[3] for st in S["dw"]] if "dw" in S else [S["xl"]])
         L.call("permute3_f32", gwo, G["pre_encode.out.weight"], d, F2, C, 1, 1)  # [n, f, c] → [n, c*F2 + f]
 
         def conv1_bwd(dx1):
@@ -419,6 +424,8 @@ class _Pass:
                 L.call("p_dwconv2d_bwd", ddw, xin, pe.conv[ci].weight.detach().contiguous(), lens[s_i + 1], dxin,
                        G[f"pre_encode.conv.{ci}.weight"], G[f"pre_encode.conv.{ci}.bias"], B, Ts[s_i + 1], Fs[s_i + 1], C)
                 dcur = dxin
+                if dbg is not None:
+                    dbg[f"dpre{s_i}"], dbg[f"ddw{s_i}"], dbg[f"dxin{s_i}"] = dpre.clone(), ddw.clone(), dxin.clone()
             conv1_bwd(dcur.view(-1, C))
         return G
 

@@ -157,10 +157,27 @@ def _time_mask(x: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
     return x * m[:, None, :, None]
 
 
-def subsampling(sd: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor, lengths: torch.Tensor, kind: str, factor: int):
+def subsampling(sd: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor, lengths: torch.Tensor, kind: str, factor: int,
+                relu_gates=None, gate_report=None):
     """ConvSubsampling.forward — subsampling.py:385-436 with MaskedConvSequential.forward :725-753.
-    x [B,T,feat] → ([B,T',d], lengths')."""
+    x [B,T,feat] → ([B,T',d], lengths').
+
+    relu_gates (test aid): list of bool tensors [B,C,T,F], one per ReLU, used INSTEAD of (x > 0).  Two fp32 implementations of
+    the same convolution disagree on the sign of pre-activations that are within rounding of zero (a few dozen of 15 M at
+    Conformer-L), and each flipped gate passes / blocks a full-size gradient — comparing gradients through ReLUs is only
+    well-posed inside the same linear region.  gate_report (list) receives (n_flipped, max |pre| among flipped, max |pre|)."""
     n = int(math.log2(factor))
+    gates = list(relu_gates) if relu_gates is not None else None
+
+    def relu(t):
+        if gates is None:
+            return F.relu(t)
+        gt = gates.pop(0).to(t.device)
+        if gate_report is not None:
+            flip = gt != (t > 0)
+            gate_report.append((int(flip.sum()), float(t.detach().abs()[flip].max()) if flip.any() else 0.0, float(t.detach().abs().max())))
+        return t * gt.to(t.dtype)
+
     cur = lengths.clone().float()
     x = x.unsqueeze(1)
     w = lambda i, s: sd[f"{prefix}conv.{i}.{s}"]
@@ -172,7 +189,7 @@ def subsampling(sd: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor, lengt
             x = F.conv2d(x, w(idx, "weight"), w(idx, "bias"), stride=2, padding=1)
             cur = torch.div(cur + 2 - 3, 2, rounding_mode="floor") + 1  # calculate_conv_output_size :720-722
             x = _time_mask(x, cur.long())
-            x = F.relu(x)
+            x = relu(x)
             idx += 2
         x = _time_mask(x, cur.long())
     elif kind == "dw_striding":
@@ -181,7 +198,7 @@ def subsampling(sd: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor, lengt
         x = F.conv2d(x, w(0, "weight"), w(0, "bias"), stride=2, padding=1)
         cur = torch.div(cur + 2 - 3, 2, rounding_mode="floor") + 1
         x = _time_mask(x, cur.long())
-        x = F.relu(x)
+        x = relu(x)
         idx = 2
         for _ in range(n - 1):
             x = _time_mask(x, cur.long())
@@ -191,7 +208,7 @@ def subsampling(sd: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor, lengt
             x = _time_mask(x, cur.long())
             x = F.conv2d(x, w(idx + 1, "weight"), w(idx + 1, "bias"))
             x = _time_mask(x, cur.long())
-            x = F.relu(x)
+            x = relu(x)
             idx += 3
         x = _time_mask(x, cur.long())
     else:
@@ -310,11 +327,13 @@ def encoder_forward(
     bn_out: Optional[dict] = None,
     return_layers: bool = False,
     use_sdpa: bool = False,
+    relu_gates=None,
+    gate_report=None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """ConformerEncoder.forward_internal — conformer_encoder.py:593-759, full-context offline path.
     audio_signal [B,feat_in,T_mel], length [B] → (outputs [B,d_model,T'], encoded_lengths [B] i64)."""
     x = audio_signal.transpose(1, 2)
-    x, length = subsampling(sd, "pre_encode.", x, length, subsampling_kind, subsampling_factor)
+    x, length = subsampling(sd, "pre_encode.", x, length, subsampling_kind, subsampling_factor, relu_gates, gate_report)
     length = length.to(torch.int64)
     B, T, _ = x.shape
     if xscaling:

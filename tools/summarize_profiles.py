@@ -114,8 +114,41 @@ def ncu_kernels():
             f.write(open(kt).read())
 
 
+def dram_traffic():
+    """profiles/dram_traffic.json: DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the `ncu --set full`
+    capture of tools/prof_kernels.py — what bench.py puts into `roofline.traffic`.  `gemm_family_cfg2` = mean over the eight
+    representative GEMM launches of a Conformer-L layer (FFN fwd / dgrad / wgrad, qkv); `mel_frontend_32x30s` = mel_frames +
+    mel_normalize of one 32 x 30 s pass."""
+    p = os.path.join(G, "prof_kernels_raw.csv")
+    if not os.path.exists(p):
+        return
+    rows = list(csv.reader(open(p)))
+    hdr = rows[0]
+    col = {h: i for i, h in enumerate(hdr)}
+    unit = {h: rows[1][i] for h, i in col.items()}
+
+    def to_bytes(r, key):
+        v = float((r[col[key]] or "0").replace(",", ""))
+        u = unit.get(key, "byte").lower()
+        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+
+    per = []
+    for r in rows[2:]:
+        name = re.sub(r"void |b2c::|\(.*", "", r[col["Kernel Name"]])[:70]
+        per.append((name, to_bytes(r, "dram__bytes_read.sum") + to_bytes(r, "dram__bytes_write.sum")))
+    gem = [b for n, b in per if n.startswith("gemm_tc_kernel")]
+    mel = [b for n, b in per if n.startswith("mel_")]
+    out = {"source": f"ncu --set full --clock-control none over tools/prof_kernels.py ({tag}); bytes per launch",
+           "gemm_family_cfg2": sum(gem) / len(gem) if gem else None,
+           "gemm_family_cfg2_detail": {f"{i}:{n}": b for i, (n, b) in enumerate(per) if n.startswith("gemm_tc_kernel")},
+           "mel_frontend_32x30s": sum(mel[-2:]) if len(mel) >= 2 else None,
+           "all": {f"{i}:{n}": b for i, (n, b) in enumerate(per)}}
+    json.dump(out, open(os.path.join(out_dir, "dram_traffic.json"), "w"), indent=1)
+
+
 launches()
 ncu_kernels()
+dram_traffic()
 for f in ("bench.log",):
     p = os.path.join(G, f)
     if os.path.exists(p):
