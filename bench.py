@@ -429,7 +429,7 @@ def run_mel_sweep(args):
             out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        _teardown(dist)
 
 
 # ------------------------------------------------------------------------------------------------ ours
@@ -669,7 +669,24 @@ def run_ours(args):
             out["gpu_eager_baseline"] = gpu_eager_baseline(args.config, dev)
         print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        _teardown(dist)
+
+
+def _teardown(dist):
+    """Leave a multi-rank run without the NCCL / CUDA-graph teardown hang: a process group that was used inside a captured graph
+    can block in destroy_process_group() or at interpreter exit (observed: every rank idle until the launcher's timeout).  All
+    ranks meet at a barrier, flush, and exit hard; a watchdog covers the barrier itself."""
+    import threading
+
+    threading.Timer(30.0, lambda: os._exit(0)).start()
+    try:
+        dist.barrier()
+        torch.cuda.synchronize()
+    except Exception:  # noqa: BLE001
+        pass
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():

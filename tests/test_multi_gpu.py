@@ -1,7 +1,9 @@
 """2-rank data-parallel correctness ON HARDWARE: gradients after the layer-wise overlapped NCCL all-reduce of
 FlatGradients == single-rank gradients of the concatenated batch.  BatchNorm runs on running statistics (eval) so the
 utterances are independent — with batch statistics the two differ by construction (SyncBatchNorm is deliberately not
-reproduced).  Needs 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_multi_gpu.py -m gpu`."""
+reproduced).  With >= 2 GPUs the ranks sit on different devices and reduce over NCCL (`gpurun --gpus 2`); on a
+one-GPU box both ranks share cuda:0 and reduce over gloo (NCCL refuses two ranks on one device) — the kernels, the flat
+buffer, the bucketing and the all-reduce calls are the same."""
 import os
 
 import pytest
@@ -44,9 +46,13 @@ def _worker(rank, world, port, out):
 
     from nemo_b200.parallel import FlatGradients, shard_batch
 
-    torch.cuda.set_device(rank)
-    dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", device_id=dev)
+    ngpu = torch.cuda.device_count()
+    dev = torch.device("cuda", rank % ngpu)
+    torch.cuda.set_device(dev)
+    if ngpu >= world:
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         enc = _build(dev)
         fg = FlatGradients(enc)
@@ -70,17 +76,31 @@ def _worker(rank, world, port, out):
             refused = True
         if rank == 0:
             out["refused"] = refused
+        dist.barrier()
+    except Exception:  # noqa: BLE001
+        import traceback
+
+        out[f"error{rank}"] = traceback.format_exc()
+        raise
     finally:
-        dist.destroy_process_group()
+        try:
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001
+            pass
 
 
-@pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
 def test_two_rank_allreduced_gradients_equal_single_rank_global_batch():
     import torch.multiprocessing as mp
 
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(2, 29533, out), nprocs=2, join=True)
+    try:
+        mp.spawn(_worker, args=(2, 29533, out), nprocs=2, join=True)
+    except Exception:  # noqa: BLE001
+        for k in ("error0", "error1"):
+            if k in out:
+                print(k, out[k])
+        raise
     dev = torch.device("cuda", 0)
     enc = _build(dev)
     x, ln, r = _data()

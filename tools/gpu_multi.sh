@@ -4,7 +4,7 @@ N=${1:-2}
 mkdir -p gpurun_out
 run() {  # name, bench args...
   name=$1; shift
-  ( timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus $N "$@" 2>&1 | grep '^{' | tail -1 ) > gpurun_out/multi_n${N}_$name.json
+  ( timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29571 bench.py --gpus $N "$@" 2>&1 | grep '^{' | tail -1 ) > gpurun_out/multi_n${N}_$name.json
   python - <<PY
 import json
 f="gpurun_out/multi_n${N}_$name.json"
@@ -23,13 +23,9 @@ if [ "$N" = "2" ]; then
 fi
 if [ "$N" = "4" ]; then
   run cfg3_weak --config 3 --steps 10 --warmup 3
-  run cfg2_weak --config 2 --steps 10 --warmup 3
   run cfg2_strong --config 2 --scaling strong --steps 10 --warmup 3
 fi
 if [ "$N" = "8" ]; then
   run cfg4_weak --config 4 --steps 10 --warmup 3
-  run cfg4_weak_eager --config 4 --steps 10 --warmup 3 --no-graph
-  run cfg2_weak --config 2 --steps 10 --warmup 3
   run cfg2_strong --config 2 --scaling strong --steps 10 --warmup 3
-  run cfg3_weak --config 3 --steps 10 --warmup 3
 fi
