@@ -39,11 +39,11 @@ long long b2c_launch_count(void);
  * multi_head_attention.py:104-123,146,300; subsampling.py:431). */
 typedef enum {
   B2C_EPI_BF16 = 0,      /* out0(bf16)[m,n] = acc + bias[n]                                               */
-  B2C_EPI_SILU = 1,      /* out0 = z = bf16(acc+bias); out1 = bf16(dropout(silu(z)))        (FFN linear1)  */
+  B2C_EPI_SILU = 1,      /* out0 = z = bf16(acc+bias); out1 = bf16(dropout(silu(acc+bias)))  (FFN linear1)  */
   B2C_EPI_RESID_F32 = 2, /* out0(f32) = (aux? aux(f32) : 0) + alpha * dropout(bf16(acc+bias))  (residual)  */
   B2C_EPI_GLU_MASK = 3,  /* interleaved (value,gate) columns: out0 = bf16(acc+bias) [M,N];
                             out1[m,n/2] = bf16(a*sigmoid(g)) * (t<len)                (pointwise_conv1+GLU) */
-  B2C_EPI_DSILU = 4,     /* out0 = bf16(dropout(bf16(acc)) * silu'(aux(bf16)[m,n]))        (FFN backward)  */
+  B2C_EPI_DSILU = 4,     /* out0 = bf16(dropout(acc) * silu'(aux(bf16)[m,n]))              (FFN backward)  */
   B2C_EPI_RELU_MASK = 5, /* out0 = bf16(relu(acc+bias)) * (t<len)                      (subsampling conv) */
   B2C_EPI_ACCUM_F32 = 6, /* out0(f32)[m,n] += alpha*acc  (split-K, atomic)             (weight gradients)  */
   B2C_EPI_RELU_BWD = 7   /* out0 = bf16(aux(bf16)[m,n] > 0 ? acc : 0)          (gradient through ReLU+mask) */
