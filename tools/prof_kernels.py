@@ -113,5 +113,19 @@ pre = B200MelPreprocessor(sample_rate=16000, window_size=0.025, window_stride=0.
 wav = (torch.rand(32, 480000, device=DEV) * 0.2 - 0.1)
 wl = torch.full((32,), 480000, dtype=torch.int64, device=DEV)
 timed("mel front-end 32x30 s (frames + normalize)", lambda: pre(input_signal=wav, length=wl), bytes_=32 * (4 * 480000 + 4 * 80 * 3001))
+# ---- dw_striding depthwise 3x3 stride-2 kernels at the FastConformer shapes (16 x 30 s per GPU, C = 256)
+Bq, Cq = 16, 256
+for (T1, F1) in ((1501, 40), (751, 20)):
+    T2, F2 = (T1 - 1) // 2 + 1, (F1 - 1) // 2 + 1
+    xin = rnd(Bq, T1, F1, Cq)
+    wq, bq_ = torch.randn(Cq, 9, device=DEV) * 0.2, torch.zeros(Cq, device=DEV)
+    lo = torch.full((Bq,), T2, dtype=torch.int32, device=DEV)
+    yq = torch.empty(Bq, T2, F2, Cq, dtype=torch.bfloat16, device=DEV)
+    dxq = torch.empty(Bq, T1, F1, Cq, dtype=torch.bfloat16, device=DEV)
+    gwq, gbq = torch.zeros(Cq, 9, device=DEV), torch.zeros(Cq, device=DEV)
+    nb_in, nb_out = Bq * T1 * F1 * Cq * 2, Bq * T2 * F2 * Cq * 2
+    timed(f"dwconv3x3s2_fwd  [{Bq},{T1},{F1},{Cq}]", lambda: L.call("dwconv3x3s2_fwd", xin, wq, bq_, lo, yq, Bq, T1, F1, Cq), bytes_=nb_in + nb_out)
+    timed(f"dwconv3x3s2_bwd  [{Bq},{T1},{F1},{Cq}] (data+weight)",
+          lambda: L.call("dwconv3x3s2_bwd", yq, xin, wq, lo, dxq, gwq, gbq, Bq, T1, F1, Cq), bytes_=3 * nb_in + 2 * nb_out)
 torch.cuda.synchronize()
 print("done")
