@@ -148,19 +148,38 @@ subsample_conv1_bwd_kernel(const float* __restrict__ mel, const bf16* __restrict
 }
 
 // depthwise Conv2d(C, 3x3, s2, p1, groups=C) on channels-last [B,T1,F1,C] → [B,T2,F2,C], + bias, output masked t2<len
-// (input is already time-masked by its producer).  thread = (channel pair, slice of the f axis); CTA = (b, t2) row.
-// With C = 256 (FastConformer) there are only 128 channel pairs: the 512 threads of a CTA split the f positions four ways
-// (`fpart`, stride `fs`) so that no thread idles and four times as many loads are in flight per row.
-constexpr int kDwThreads = 512;
+// (input is already time-masked by its producer).  thread = (channel pair, row slice); CTA = kDwRows time rows of one batch
+// item, so the 18 strided weight loads of a thread are amortised over kDwRows / rs rows x F positions (one row per CTA made
+// that prologue a third of the kernel; splitting the f axis over more threads instead made it worse — measured).
+// With C = 256 (FastConformer) the 128 channel pairs leave room for rs = 2 row slices in a 256-thread CTA.
+constexpr int kDwThreads = 256;
+constexpr int kDwRows = 8;
+
+struct DwMap {
+  int CP, rs, rpart, cp0, cstep;
+  bool idle;
+};
+__device__ __forceinline__ DwMap dw_map(int C) {
+  DwMap m;
+  m.CP = C >> 1;
+  if (m.CP >= (int)blockDim.x) {  // more channel pairs than threads: loop over them, one row slice
+    m.rs = 1; m.rpart = 0; m.cp0 = (int)threadIdx.x; m.cstep = (int)blockDim.x; m.idle = false;
+  } else {
+    m.rs = (int)blockDim.x / m.CP; m.rpart = (int)threadIdx.x / m.CP; m.cp0 = (int)threadIdx.x % m.CP; m.cstep = m.CP;
+    m.idle = m.rpart >= m.rs;
+  }
+  return m;
+}
+
 __global__ void __launch_bounds__(kDwThreads)
 dwconv3x3s2_fwd_kernel(const bf16* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                        const int32_t* __restrict__ len_out, bf16* __restrict__ out, int T1, int F1, int C, int T2, int F2) {
-  const int t2 = blockIdx.x, b = blockIdx.y;
-  const bool valid = len_out ? (t2 < len_out[b]) : true;
-  const int CP = C >> 1, fs = max(1, (int)blockDim.x / CP);
-  const int fpart = (CP >= (int)blockDim.x) ? 0 : (int)threadIdx.x / CP;
-  if (fpart >= fs) return;
-  for (int cp = (CP >= (int)blockDim.x) ? (int)threadIdx.x : (int)threadIdx.x % CP; cp < CP; cp += (CP >= (int)blockDim.x) ? (int)blockDim.x : CP) {
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * kDwRows, r1 = min(T2, r0 + kDwRows);
+  const int lout = len_out ? len_out[b] : T2;
+  const DwMap m = dw_map(C);
+  if (m.idle) return;
+  for (int cp = m.cp0; cp < m.CP; cp += m.cstep) {
     const int c = cp * 2;
     float w0[9], w1[9];
 #pragma unroll
@@ -169,23 +188,26 @@ dwconv3x3s2_fwd_kernel(const bf16* __restrict__ in, const float* __restrict__ w,
       w1[j] = bf16_round(w[(size_t)(c + 1) * 9 + j]);
     }
     const float b0 = bias[c], b1 = bias[c + 1];
-    for (int f2 = fpart; f2 < F2; f2 += fs) {
-      float a0 = 0.f, a1 = 0.f;
+    for (int t2 = r0 + m.rpart; t2 < r1; t2 += m.rs) {
+      const bool valid = t2 < lout;
+      for (int f2 = 0; f2 < F2; ++f2) {
+        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const int t = 2 * t2 - 1 + kh;
-        if (t < 0 || t >= T1) continue;
+        for (int kh = 0; kh < 3; ++kh) {
+          const int t = 2 * t2 - 1 + kh;
+          if (t < 0 || t >= T1) continue;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int f = 2 * f2 - 1 + kw;
-          if (f < 0 || f >= F1) continue;
-          const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(in + (((size_t)b * T1 + t) * F1 + f) * C + c));
-          a0 = fmaf(w0[kh * 3 + kw], x.x, a0);
-          a1 = fmaf(w1[kh * 3 + kw], x.y, a1);
+          for (int kw = 0; kw < 3; ++kw) {
+            const int f = 2 * f2 - 1 + kw;
+            if (f < 0 || f >= F1) continue;
+            const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(in + (((size_t)b * T1 + t) * F1 + f) * C + c));
+            a0 = fmaf(w0[kh * 3 + kw], x.x, a0);
+            a1 = fmaf(w1[kh * 3 + kw], x.y, a1);
+          }
         }
+        const uint32_t o = valid ? pack_bf16(a0 + b0, a1 + b1) : 0u;
+        *reinterpret_cast<uint32_t*>(out + (((size_t)b * T2 + t2) * F2 + f2) * C + c) = o;
       }
-      const uint32_t o = valid ? pack_bf16(a0 + b0, a1 + b1) : 0u;
-      *reinterpret_cast<uint32_t*>(out + (((size_t)b * T2 + t2) * F2 + f2) * C + c) = o;
     }
   }
 }
@@ -196,12 +218,12 @@ __global__ void __launch_bounds__(kDwThreads)
 dwconv3x3s2_bwd_data_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ w,
                             const int32_t* __restrict__ len_out, bf16* __restrict__ dx, int T1, int F1, int C, int T2,
                             int F2) {
-  const int t1 = blockIdx.x, b = blockIdx.y;
+  const int b = blockIdx.y;
+  const int r0 = blockIdx.x * kDwRows, r1 = min(T1, r0 + kDwRows);
   const int lout = len_out ? len_out[b] : T2;
-  const int CP = C >> 1, fs = max(1, (int)blockDim.x / CP);
-  const int fpart = (CP >= (int)blockDim.x) ? 0 : (int)threadIdx.x / CP;
-  if (fpart >= fs) return;
-  for (int cp = (CP >= (int)blockDim.x) ? (int)threadIdx.x : (int)threadIdx.x % CP; cp < CP; cp += (CP >= (int)blockDim.x) ? (int)blockDim.x : CP) {
+  const DwMap m = dw_map(C);
+  if (m.idle) return;
+  for (int cp = m.cp0; cp < m.CP; cp += m.cstep) {
     const int c = cp * 2;
     float w0[9], w1[9];
 #pragma unroll
@@ -209,92 +231,89 @@ dwconv3x3s2_bwd_data_kernel(const bf16* __restrict__ dy, const bf16* __restrict_
       w0[j] = bf16_round(w[(size_t)c * 9 + j]);
       w1[j] = bf16_round(w[(size_t)(c + 1) * 9 + j]);
     }
-    for (int f1 = fpart; f1 < F1; f1 += fs) {
-      float a0 = 0.f, a1 = 0.f;
+    for (int t1 = r0 + m.rpart; t1 < r1; t1 += m.rs) {
+      for (int f1 = 0; f1 < F1; ++f1) {
+        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const int tn = t1 + 1 - kh;
-        if (tn < 0 || (tn & 1)) continue;
-        const int t2 = tn >> 1;
-        if (t2 >= T2 || t2 >= lout) continue;
+        for (int kh = 0; kh < 3; ++kh) {
+          const int tn = t1 + 1 - kh;
+          if (tn < 0 || (tn & 1)) continue;
+          const int t2 = tn >> 1;
+          if (t2 >= T2 || t2 >= lout) continue;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int fn = f1 + 1 - kw;
-          if (fn < 0 || (fn & 1)) continue;
-          const int f2 = fn >> 1;
-          if (f2 >= F2) continue;
-          const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(dy + (((size_t)b * T2 + t2) * F2 + f2) * C + c));
-          a0 = fmaf(w0[kh * 3 + kw], g.x, a0);
-          a1 = fmaf(w1[kh * 3 + kw], g.y, a1);
+          for (int kw = 0; kw < 3; ++kw) {
+            const int fn = f1 + 1 - kw;
+            if (fn < 0 || (fn & 1)) continue;
+            const int f2 = fn >> 1;
+            if (f2 >= F2) continue;
+            const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(dy + (((size_t)b * T2 + t2) * F2 + f2) * C + c));
+            a0 = fmaf(w0[kh * 3 + kw], g.x, a0);
+            a1 = fmaf(w1[kh * 3 + kw], g.y, a1);
+          }
         }
+        const size_t o = (((size_t)b * T1 + t1) * F1 + f1) * C + c;
+        const float2 xv = unpack_bf16(*reinterpret_cast<const uint32_t*>(x + o));
+        *reinterpret_cast<uint32_t*>(dx + o) = pack_bf16(xv.x > 0.f ? a0 : 0.f, xv.y > 0.f ? a1 : 0.f);
       }
-      const size_t o = (((size_t)b * T1 + t1) * F1 + f1) * C + c;
-      const float2 xv = unpack_bf16(*reinterpret_cast<const uint32_t*>(x + o));
-      *reinterpret_cast<uint32_t*>(dx + o) = pack_bf16(xv.x > 0.f ? a0 : 0.f, xv.y > 0.f ? a1 : 0.f);
     }
   }
 }
 
 // weight / bias gradients of the depthwise 3x3 s2 conv: dw[c,kh,kw] += sum dy[b,t2,f2,c] * x[b,2t2+kh-1,2f2+kw-1,c]
+// (CP * rs == blockDim.x is arranged by the launcher; the row slices of a channel pair are summed through shared memory, then
+// one atomic per (channel, tap) per CTA)
 __global__ void __launch_bounds__(kDwThreads)
 dwconv3x3s2_bwd_weight_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const int32_t* __restrict__ len_out,
                               float* __restrict__ dw, float* __restrict__ dbias, int T1, int F1, int C, int T2, int F2,
                               int rows_per_cta) {
+  __shared__ float red[kDwThreads * 20];
   const int b = blockIdx.y;
   const int lout = len_out ? min(len_out[b], T2) : T2;
   const int t2_0 = blockIdx.x * rows_per_cta, t2_1 = min(lout, t2_0 + rows_per_cta);
-  // thread = (f-slice q, channel pair): CP * fs == blockDim.x is required by the launcher (C/2 divides the CTA size)
-  const int CP = C >> 1, fs = (int)blockDim.x / CP;
-  const int fpart = (int)threadIdx.x / CP;
-  {
-    const int cp = (int)threadIdx.x % CP;
-    const int c = cp * 2;
-    float g0[9], g1[9], d0 = 0.f, d1 = 0.f;
+  const int CP = C >> 1, rs = (int)blockDim.x / CP;
+  const int rpart = (int)threadIdx.x / CP, cp = (int)threadIdx.x % CP;
+  const int c = cp * 2;
+  float g0[9], g1[9], d0 = 0.f, d1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 9; ++j) g0[j] = g1[j] = 0.f;
-    for (int t2 = t2_0; t2 < t2_1; ++t2) {
-      for (int f2 = fpart; f2 < F2; f2 += fs) {
-        const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(dy + (((size_t)b * T2 + t2) * F2 + f2) * C + c));
-        d0 += g.x; d1 += g.y;
+  for (int j = 0; j < 9; ++j) g0[j] = g1[j] = 0.f;
+  for (int t2 = t2_0 + rpart; t2 < t2_1; t2 += rs) {
+    for (int f2 = 0; f2 < F2; ++f2) {
+      const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(dy + (((size_t)b * T2 + t2) * F2 + f2) * C + c));
+      d0 += g.x; d1 += g.y;
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          const int t = 2 * t2 - 1 + kh;
-          if (t < 0 || t >= T1) continue;
+      for (int kh = 0; kh < 3; ++kh) {
+        const int t = 2 * t2 - 1 + kh;
+        if (t < 0 || t >= T1) continue;
 #pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const int f = 2 * f2 - 1 + kw;
-            if (f < 0 || f >= F1) continue;
-            const float2 xv = unpack_bf16(*reinterpret_cast<const uint32_t*>(x + (((size_t)b * T1 + t) * F1 + f) * C + c));
-            g0[kh * 3 + kw] = fmaf(g.x, xv.x, g0[kh * 3 + kw]);
-            g1[kh * 3 + kw] = fmaf(g.y, xv.y, g1[kh * 3 + kw]);
-          }
+        for (int kw = 0; kw < 3; ++kw) {
+          const int f = 2 * f2 - 1 + kw;
+          if (f < 0 || f >= F1) continue;
+          const float2 xv = unpack_bf16(*reinterpret_cast<const uint32_t*>(x + (((size_t)b * T1 + t) * F1 + f) * C + c));
+          g0[kh * 3 + kw] = fmaf(g.x, xv.x, g0[kh * 3 + kw]);
+          g1[kh * 3 + kw] = fmaf(g.y, xv.y, g1[kh * 3 + kw]);
         }
       }
     }
-    // one atomic per (channel, tap) per CTA: the f-slices of a channel pair are summed through shared memory first
-    // (global atomics were the bound of this kernel: every thread used to issue 20 of them)
-    __shared__ float red[kDwThreads * 20];
-    float* mine = red + threadIdx.x * 20;
+  }
+  float* mine = red + threadIdx.x * 20;
 #pragma unroll
-    for (int j = 0; j < 9; ++j) { mine[j] = g0[j]; mine[9 + j] = g1[j]; }
-    mine[18] = d0; mine[19] = d1;
-    __syncthreads();
-    if (fpart == 0 && t2_1 > t2_0) {
-      float acc[20];
+  for (int j = 0; j < 9; ++j) { mine[j] = g0[j]; mine[9 + j] = g1[j]; }
+  mine[18] = d0; mine[19] = d1;
+  __syncthreads();
+  if (rpart == 0 && t2_1 > t2_0) {
+    float acc[20];
 #pragma unroll
-      for (int j = 0; j < 20; ++j) acc[j] = 0.f;
-      for (int q = 0; q < fs; ++q)
+    for (int j = 0; j < 20; ++j) acc[j] = 0.f;
+    for (int q = 0; q < rs; ++q)
 #pragma unroll
-        for (int j = 0; j < 20; ++j) acc[j] += red[(q * CP + cp) * 20 + j];
+      for (int j = 0; j < 20; ++j) acc[j] += red[(q * CP + cp) * 20 + j];
 #pragma unroll
-      for (int j = 0; j < 9; ++j) {
-        atomicAdd(dw + (size_t)c * 9 + j, acc[j]);
-        atomicAdd(dw + (size_t)(c + 1) * 9 + j, acc[9 + j]);
-      }
-      atomicAdd(dbias + c, acc[18]);
-      atomicAdd(dbias + c + 1, acc[19]);
+    for (int j = 0; j < 9; ++j) {
+      atomicAdd(dw + (size_t)c * 9 + j, acc[j]);
+      atomicAdd(dw + (size_t)(c + 1) * 9 + j, acc[9 + j]);
     }
-    __syncthreads();
+    atomicAdd(dbias + c, acc[18]);
+    atomicAdd(dbias + c + 1, acc[19]);
   }
 }
 
@@ -341,7 +360,7 @@ extern "C" int b2c_dwconv3x3s2_fwd(const void* in_bf16, const float* w, const fl
                                    void* out_bf16, int B, int T1, int F1, int C, void* stream) {
   B2C_REQUIRE(C % 2 == 0 && B > 0 && T1 > 0 && F1 > 0, "dwconv3x3s2_fwd: bad shape");
   const int T2 = (T1 + 2 - 3) / 2 + 1, F2 = (F1 + 2 - 3) / 2 + 1;
-  dwconv3x3s2_fwd_kernel<<<dim3(T2, B), kDwThreads, 0, (cudaStream_t)stream>>>(
+  dwconv3x3s2_fwd_kernel<<<dim3((T2 + kDwRows - 1) / kDwRows, B), kDwThreads, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const bf16*>(in_bf16), w, bias, len_out, reinterpret_cast<bf16*>(out_bf16), T1, F1, C, T2, F2);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
@@ -351,7 +370,7 @@ extern "C" int b2c_dwconv3x3s2_bwd(const void* dy_bf16, const void* x_bf16, cons
                                    void* dx_bf16, float* dw, float* dbias, int B, int T1, int F1, int C, void* stream) {
   B2C_REQUIRE(C % 2 == 0 && B > 0 && T1 > 0 && F1 > 0, "dwconv3x3s2_bwd: bad shape");
   const int T2 = (T1 + 2 - 3) / 2 + 1, F2 = (F1 + 2 - 3) / 2 + 1;
-  dwconv3x3s2_bwd_data_kernel<<<dim3(T1, B), kDwThreads, 0, (cudaStream_t)stream>>>(
+  dwconv3x3s2_bwd_data_kernel<<<dim3((T1 + kDwRows - 1) / kDwRows, B), kDwThreads, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const bf16*>(dy_bf16), reinterpret_cast<const bf16*>(x_bf16), w, len_out,
       reinterpret_cast<bf16*>(dx_bf16), T1, F1, C, T2, F2);
   B2C_LAUNCH_CHECK();

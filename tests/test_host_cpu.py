@@ -260,3 +260,56 @@ def test_nemo_checkpoint_round_trip(tmp_path):
         tar.add(str(src / "model_weights.ckpt"), arcname="../model_weights.ckpt")
     with pytest.raises(FileNotFoundError):
         ck.load_nemo(evil)
+
+
+def test_grad_layout_keeps_qkv_adjacent_and_block_views():
+    """parallel.grad_layout: inside every attention block linear_q/k/v weights (and biases) are adjacent in the flat gradient
+    buffer (the fused q|k|v weight gradient is one [3d, d] GEMM output written in place); a frozen member breaks the block."""
+    from nemo_b200.encoder import B200ConformerEncoder
+    from nemo_b200.parallel import FlatGradients, grad_layout
+
+    enc = B200ConformerEncoder(feat_in=80, n_layers=2, d_model=128, n_heads=2, conv_kernel_size=9)
+    names = [n for n, _ in grad_layout(enc.named_parameters())]
+    assert sorted(names) == sorted(n for n, _ in enc.named_parameters())
+    i = names.index("layers.1.self_attn.linear_q.weight")
+    assert names[i:i + 6] == [f"layers.1.self_attn.linear_{x}.{y}" for y in ("weight", "bias") for x in ("q", "k", "v")]
+    fg = FlatGradients(enc)
+    blk = fg.block("layers.0.self_attn.linear_q.weight", 3)
+    assert blk is not None and blk.numel() == 3 * 128 * 128
+    assert blk.data_ptr() == enc.layers[0].self_attn.linear_q.weight.grad.data_ptr()
+    assert enc.layers[0].self_attn.linear_v.weight.grad.data_ptr() == blk.data_ptr() + 2 * 128 * 128 * 4
+    lo, hi = fg.span("layers.1.")
+    assert hi - lo == sum(p.numel() for p in enc.layers[1].parameters())  # a layer stays one contiguous all-reduce span
+    enc2 = B200ConformerEncoder(feat_in=80, n_layers=1, d_model=128, n_heads=2, conv_kernel_size=9)
+    enc2.layers[0].self_attn.linear_k.weight.requires_grad_(False)
+    fg2 = FlatGradients(enc2)
+    b2 = fg2.block("layers.0.self_attn.linear_q.weight", 3)
+    assert b2 is None or b2.numel() != 3 * 128 * 128
+
+
+def test_noam_restatement_matches_the_reference_scheduler():
+    """optim.noam_lr (what B200FusedAdamW evaluates on the device) vs NoamAnnealing._noam_annealing of the reference
+    (nemo/core/optim/lr_scheduler.py:566-575), extracted from the source file when /root/reference is present."""
+    import ast
+
+    from nemo_b200.optim import noam_lr
+
+    path = "/root/reference/nemo/core/optim/lr_scheduler.py"
+    if not os.path.exists(path):
+        pytest.skip("/root/reference not present (GPU box)")
+    src = open(path).read()
+    tree = ast.parse(src)
+    fn = next(n for c in tree.body if isinstance(c, ast.ClassDef) and c.name == "NoamAnnealing" for n in c.body
+              if isinstance(n, ast.FunctionDef) and n.name == "_noam_annealing")
+    ns = {}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)  # the reference's own method body, unmodified
+
+    class S:  # the attributes the method reads (NoamAnnealing.__init__, :530-546)
+        pass
+
+    for d_model, warm, min_lr in ((512, 10000, 1e-6), (1024, 25000, 1e-6), (176, 0, 1e-5)):
+        s = S()
+        s._normalize, s.warmup_steps, s.min_lr = d_model ** -0.5, warm, min_lr
+        for opt_step in (1, 2, 3, 100, 9999, 10000, 10001, 10002, 50000, 10 ** 7):
+            want = ns["_noam_annealing"](s, initial_lr=2.0, step=max(1, opt_step - 1))  # get_lr: step = max(1, last_epoch)
+            assert noam_lr(2.0, d_model, warm, min_lr, opt_step) == pytest.approx(want, rel=1e-12), (d_model, opt_step)
