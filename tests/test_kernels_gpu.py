@@ -565,3 +565,33 @@ def test_gemm_epilogues_on_odd_tile_counts_narrow_n_and_shared_dropout_masks():
     r = torch.empty_like(x)
     L.gemm(A, B, M, N, K, K, K, 0, 0, L.EPI_RESID_F32, out0=r, aux=x, bias=bias, alpha=0.5)
     report("resid_odd", r, x + 0.5 * zr, 5e-3)
+
+
+@pytest.mark.parametrize("B,T1,F1,C", [(3, 101, 20, 64), (2, 203, 40, 256), (2, 77, 10, 24)])
+def test_depthwise_3x3_stride2_kernels_vs_torch(B, T1, F1, C):
+    """dw_striding stages (subsampling.py:142-215): depthwise Conv2d(C, 3x3, s2, p1, groups=C) + bias with the output time mask,
+    its data gradient (through the producer's ReLU gate) and weight / bias gradients against F.conv2d autograd on the same
+    bf16-rounded operands.  C = 64 / 256 take the 8-channel kernels, C = 24 (C/8 = 3 does not divide the CTA) the 2-channel ones."""
+    Fn = torch.nn.functional
+    T2, F2 = (T1 - 1) // 2 + 1, (F1 - 1) // 2 + 1
+    lin = torch.tensor([T1, max(T1 - 31, 3), 9][:B], device=DEV)
+    lout = ((lin - 1) // 2 + 1).to(torch.int32)
+    x = torch.relu(rnd(B, T1, F1, C)) * (torch.arange(T1, device=DEV)[None, :] < lin[:, None]).float()[:, :, None, None]
+    x16 = x.to(torch.bfloat16)
+    w, bias = rnd(C, 1, 3, 3, scale=0.3, seed=2), rnd(C, scale=0.1, seed=3)
+    y = torch.empty(B, T2, F2, C, dtype=torch.bfloat16, device=DEV)
+    L.call("dwconv3x3s2_fwd", x16, w.contiguous(), bias, lout, y, B, T1, F1, C)
+    xr = x16.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.to(torch.bfloat16).float().requires_grad_(True)
+    br = bias.clone().requires_grad_(True)
+    m_out = (torch.arange(T2, device=DEV)[None, :] < lout[:, None]).float()[:, None, :, None]
+    yr = Fn.conv2d(xr, wr, br, stride=2, padding=1, groups=C) * m_out
+    report(f"dw3x3_fwd_C{C}", y, yr.detach().permute(0, 2, 3, 1), 1e-2)
+    dy = rnd(B, T2, F2, C, seed=7).to(torch.bfloat16)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    dx = torch.full((B, T1, F1, C), 7.0, dtype=torch.bfloat16, device=DEV)
+    dw, db = torch.zeros(C, 9, device=DEV), torch.zeros(C, device=DEV)
+    L.call("dwconv3x3s2_bwd", dy, x16, w.contiguous(), lout, dx, dw, db, B, T1, F1, C)
+    report(f"dw3x3_bwd_dx_C{C}", dx, xr.grad.permute(0, 2, 3, 1) * (x16.float() > 0), 1.5e-2)
+    report(f"dw3x3_bwd_dw_C{C}", dw.view(C, 1, 3, 3), wr.grad, 1e-2)
+    report(f"dw3x3_bwd_db_C{C}", db, br.grad, 1e-2)
