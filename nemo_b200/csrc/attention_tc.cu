@@ -120,6 +120,12 @@ __device__ __forceinline__ void band_shift(uint32_t (&x)[CW + 32], int sh) {
   for (int k = 0; k < CW; ++k) x[k] = (sh & 1) ? x[k + 1] : x[k];
 }
 
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+
 // write 8 bf16 (one 16-byte chunk `chunk` of row `row`) into a [rows x 64] K-major tile with the 128 B UMMA swizzle
 __device__ __forceinline__ void st_sw128(uint8_t* tile, int row, int chunk, uint4 v) {
   sts128(smem_u32(tile) + row * 128 + ((chunk ^ (row & 7)) << 4), v);
@@ -127,12 +133,30 @@ __device__ __forceinline__ void st_sw128(uint8_t* tile, int row, int chunk, uint
 
 // NT softmax threads per query row (NT * 4 softmax warps).  2 and 4 measure the same on B200: the kernel is bound by the
 // instruction issue rate of the softmax / skew / dropout arithmetic, not by latency
-template <int NT>
+// SKS (skew through shared memory): instead of the 5-stage register barrel shift (190 selects per thread and key tile), every
+// softmax thread parks the 64 band columns it pulled from TMEM in its own padded shared-memory row (16 x STS.128) and reads
+// the 32 it needs back at its lane-dependent offset (32 x LDS.32, bank-conflict free: row pitch 68 words).  The 68 KB this
+// takes are paid for with one TMA stage (2 instead of 3).  Selected with B2C_ATTN_SKEW=smem (NT = 2 only).
+template <int NT, bool SKS>
+struct FwdLayout {
+  static constexpr int kStg = SKS ? 2 : atc::kStages;
+  static constexpr int kRowW = atc::BKV / NT + 32 + 4;  // words per softmax thread
+  static constexpr int kBar = atc::kOffStage + kStg * atc::kStageBytes;
+  static constexpr int kMax = kBar + 256;
+  static constexpr int kSkew = kMax + 3 * 4 * 128 * 4;
+  static constexpr int kTotal = kSkew + (SKS ? NT * 128 * kRowW * 4 : 0) + 1024;
+};
+
+template <int NT, bool SKS = false>
 __global__ void __launch_bounds__(128 + NT * 128, 1)
 relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                           const __grid_constant__ CUtensorMap tmP, const AttnArgs a, bf16* __restrict__ ctx,
                           float* __restrict__ ctx32, float* __restrict__ lse_out) {
   using namespace atc;
+  using FL = FwdLayout<NT, SKS>;
+  constexpr int kStages = FL::kStg;   // shadows atc::kStages
+  constexpr int kOffBar = FL::kBar;   // ... and the offsets that depend on it
+  constexpr int kOffMax = FL::kMax;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kOffBar);
@@ -292,7 +316,16 @@ relpos_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(sr_free);
-        band_shift<CW>(x, sh);
+        if constexpr (SKS) {
+          const uint32_t rowb = smem_u32(smem + FL::kSkew) + (uint32_t)((((warp - 4) * 32 + lane) * FL::kRowW) * 4);
+#pragma unroll
+          for (int c4 = 0; c4 < (CW + 32) / 4; ++c4)
+            sts128(rowb + c4 * 16, make_uint4(x[4 * c4], x[4 * c4 + 1], x[4 * c4 + 2], x[4 * c4 + 3]));
+#pragma unroll
+          for (int k = 0; k < CW; ++k) x[k] = lds32(rowb + (uint32_t)((sh + k) * 4));
+        } else {
+          band_shift<CW>(x, sh);
+        }
 #pragma unroll
         for (int k = 0; k < CW; ++k) v[k] = __uint_as_float(sa[k]) + __uint_as_float(x[k]);
       }
@@ -430,15 +463,20 @@ int launch_relpos_attn_fwd_tc(const AttnArgs& a, bf16* ctx, float* ctx32, float*
     if (rc) return rc;
   }
   static int nt = 0;  // softmax threads per row: 2 (default) or 4 (B2C_ATTN_NT=4; measured equal: issue-slot bound)
+  static int sks = 0;  // B2C_ATTN_SKEW=smem: positional-band skew through shared memory (NT = 2)
   if (nt == 0) {
     const char* e = getenv("B2C_ATTN_NT");
     nt = (e && atoi(e) == 4) ? 4 : 2;
-    B2C_CUDA(cudaFuncSetAttribute(relpos_attn_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-    B2C_CUDA(cudaFuncSetAttribute(relpos_attn_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    const char* k = getenv("B2C_ATTN_SKEW");
+    sks = (nt == 2 && k && !strcmp(k, "smem")) ? 1 : 0;
+    B2C_CUDA(cudaFuncSetAttribute(relpos_attn_fwd_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdLayout<2, false>::kTotal));
+    B2C_CUDA(cudaFuncSetAttribute(relpos_attn_fwd_tc_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdLayout<4, false>::kTotal));
+    B2C_CUDA(cudaFuncSetAttribute(relpos_attn_fwd_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdLayout<2, true>::kTotal));
   }
   const dim3 grid((a.T + BQ - 1) / BQ, a.H, a.B);
-  if (nt == 2) relpos_attn_fwd_tc_kernel<2><<<grid, 128 + 2 * 128, kSmem, st>>>(tk, tv, tp, a, ctx, ctx32, lse);
-  else relpos_attn_fwd_tc_kernel<4><<<grid, 128 + 4 * 128, kSmem, st>>>(tk, tv, tp, a, ctx, ctx32, lse);
+  if (sks) relpos_attn_fwd_tc_kernel<2, true><<<grid, 128 + 2 * 128, FwdLayout<2, true>::kTotal, st>>>(tk, tv, tp, a, ctx, ctx32, lse);
+  else if (nt == 2) relpos_attn_fwd_tc_kernel<2, false><<<grid, 128 + 2 * 128, FwdLayout<2, false>::kTotal, st>>>(tk, tv, tp, a, ctx, ctx32, lse);
+  else relpos_attn_fwd_tc_kernel<4, false><<<grid, 128 + 4 * 128, FwdLayout<4, false>::kTotal, st>>>(tk, tv, tp, a, ctx, ctx32, lse);
   B2C_LAUNCH_CHECK();
   return B2C_OK;
 }
