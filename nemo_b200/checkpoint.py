@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import io
 import os
+import re
 import tarfile
 from typing import Dict, Optional, Tuple
 
@@ -89,13 +90,55 @@ def restore(path: str, preprocessor=None, encoder=None, decoder=None, strict: bo
     return cfg
 
 
+_INTERP = re.compile(r"^\$\{([\w\.]+)\}$")
+
+
+def resolve_config(cfg, root=None, _depth=0):
+    """Resolve OmegaConf-style absolute interpolations (`${model.preprocessor.features}`) in a plain-YAML config tree.  A `.nemo`
+    file stores its config already resolved (save_restore_connector.py:590-591, `resolve=True`); the training YAMLs under
+    examples/asr/conf/ do not.  Only whole-value `${a.b.c}` references are handled (all these configs use); anything else is
+    left as it is."""
+    root = cfg if root is None else root
+    if _depth > 8:
+        return cfg
+    if isinstance(cfg, dict):
+        return {k: resolve_config(v, root, _depth) for k, v in cfg.items()}
+    if isinstance(cfg, list):
+        return [resolve_config(v, root, _depth) for v in cfg]
+    if isinstance(cfg, str):
+        m = _INTERP.match(cfg)
+        if m:
+            node = root
+            for part in m.group(1).split("."):
+                if not isinstance(node, dict) or part not in node:
+                    return cfg
+                node = node[part]
+            return resolve_config(node, root, _depth + 1)
+    return cfg
+
+
+def _kwargs(cfg) -> dict:
+    return {k: v for k, v in dict(cfg).items() if k != "_target_"}
+
+
 def encoder_from_config(cfg: dict):
-    """Instantiate B200ConformerEncoder from the `encoder:` section of a NeMo model config (the `_target_` key names the
-    reference class and is dropped — common.py:60-100 would not let a YAML name ours anyway)."""
+    """Instantiate B200ConformerEncoder from the (resolved) `encoder:` section of a NeMo model config (the `_target_` key names
+    the reference class and is dropped — common.py:60-100 would not let a YAML name ours anyway)."""
     from .encoder import B200ConformerEncoder
 
-    kw = {k: v for k, v in dict(cfg).items() if k != "_target_"}
-    return B200ConformerEncoder(**kw)
+    return B200ConformerEncoder(**_kwargs(cfg))
+
+
+def preprocessor_from_config(cfg: dict):
+    from .preprocessor import B200MelPreprocessor
+
+    return B200MelPreprocessor(**_kwargs(cfg))
+
+
+def decoder_from_config(cfg: dict):
+    from .decoder import B200ConvASRDecoder
+
+    return B200ConvASRDecoder(**_kwargs(cfg))
 
 
 def save_nemo(path: str, config, preprocessor=None, encoder=None, decoder=None, extra: Optional[Dict[str, torch.Tensor]] = None):

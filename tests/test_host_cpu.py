@@ -313,3 +313,28 @@ def test_noam_restatement_matches_the_reference_scheduler():
         for opt_step in (1, 2, 3, 100, 9999, 10000, 10001, 10002, 50000, 10 ** 7):
             want = ns["_noam_annealing"](s, initial_lr=2.0, step=max(1, opt_step - 1))  # get_lr: step = max(1, last_epoch)
             assert noam_lr(2.0, d_model, warm, min_lr, opt_step) == pytest.approx(want, rel=1e-12), (d_model, opt_step)
+
+
+@pytest.mark.parametrize("rel,params_m", [("examples/asr/conf/conformer/conformer_ctc_bpe.yaml", 121.44),
+                                          ("examples/asr/conf/fastconformer/fast-conformer_ctc_bpe.yaml", None),
+                                          ("examples/asr/conf/conformer/conformer_transducer_bpe.yaml", None)])
+def test_modules_instantiate_from_the_reference_training_yamls(rel, params_m):
+    """the encoder / preprocessor sections of the reference's shipped training configs (with their `${...}` interpolations
+    resolved) are accepted kwarg-for-kwarg by the B200 modules; Conformer-CTC-Large has the 121.44 M encoder parameters of
+    BASELINE.md §2"""
+    import yaml
+
+    from nemo_b200 import checkpoint as ck
+
+    path = os.path.join("/root/reference", rel)
+    if not os.path.exists(path):
+        pytest.skip("/root/reference not present (GPU box)")
+    cfg = ck.resolve_config(yaml.safe_load(open(path)))
+    m = cfg["model"]
+    assert m["encoder"]["feat_in"] == 80 and m["preprocessor"]["sample_rate"] == 16000
+    enc = ck.encoder_from_config(m["encoder"])
+    pre = ck.preprocessor_from_config(m["preprocessor"])
+    assert pre.featurizer.nfilt == 80 and pre.featurizer.n_fft == 512 and pre.featurizer.hop_length == 160
+    assert enc.n_layers == m["encoder"]["n_layers"] and enc.subsampling == m["encoder"]["subsampling"]
+    if params_m is not None:
+        assert abs(sum(p.numel() for p in enc.parameters()) / 1e6 - params_m) < 0.01
