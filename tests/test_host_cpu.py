@@ -86,12 +86,20 @@ def test_shard_batch_partitions_the_global_batch():
         assert max(sizes) - min(sizes) <= 1
 
 
-def _dp_worker(rank, world, port, q):
+def _dp_worker(rank, world, port, q, bucket_bytes=96 << 20, defer=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(0)
     enc = B200ConformerEncoder(feat_in=80, n_layers=2, d_model=128, n_heads=2, conv_kernel_size=9)
-    fg = FlatGradients(enc)
+    fg = FlatGradients(enc, bucket_bytes=bucket_bytes, defer=defer)
+    calls = []
+    real = dist.all_reduce
+
+    def counting(t, *a, **k):
+        calls.append(t.numel())
+        return real(t, *a, **k)
+
+    dist.all_reduce = counting
     assert all(p.grad.data_ptr() >= fg.flat.data_ptr() for p in enc.parameters())
     # emulate the backward orchestration: last layer first, each layer's slice all-reduced as soon as it is "ready"
     g = torch.Generator().manual_seed(100 + rank)
@@ -105,22 +113,27 @@ def _dp_worker(rank, world, port, q):
     ok = torch.allclose(fg.flat, expect, atol=1e-6)
     covered = sorted(fg.span(p) for p in ("pre_encode.", "layers.0.", "layers.1."))
     contiguous = covered[0][0] == 0 and covered[-1][1] == fg.flat.numel() and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
-    q.put((rank, bool(ok), bool(contiguous), fg.loss_scale()))
+    # every element is reduced exactly once, whatever the bucketing
+    q.put((rank, bool(ok), bool(contiguous), fg.loss_scale(), len(calls), sum(calls) == fg.flat.numel()))
+    dist.all_reduce = real
     dist.destroy_process_group()
 
 
-def test_flat_gradient_allreduce_gloo_world2():
+@pytest.mark.parametrize("bucket_bytes,defer,n_calls", [(96 << 20, False, 1), (1, False, 3), (96 << 20, True, 1)])
+def test_flat_gradient_allreduce_gloo_world2(bucket_bytes, defer, n_calls):
+    """layer slices finished by the backward are coalesced into buckets of >= bucket_bytes (one call for this small model, one per
+    layer with bucket_bytes = 1); defer=True reduces the whole buffer once in finish() (gradient accumulation)"""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + (7 if defer else 0) + (13 if bucket_bytes == 1 else 0)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q, bucket_bytes, defer)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(2)]
     for p in procs:
         p.join(timeout=60)
-    for rank, ok, contiguous, scale in res:
-        assert ok and contiguous and scale == 0.5, (rank, ok, contiguous, scale)
+    for rank, ok, contiguous, scale, calls, once in res:
+        assert ok and contiguous and scale == 0.5 and calls == n_calls and once, (rank, ok, contiguous, scale, calls, once)
 
 
 def test_bench_work_model_matches_baseline_md():
